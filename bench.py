@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- element x pixel ray-solves/s of the TOF table hot path.
+
+    python bench.py --gpus N --steps K --warmup W          # product arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N ...          # CPU arm (oracle port on the host cores)
+
+A "step" is one pass of the hot path (main_rt.py:464-501: trace the K rays of
+the shot and assemble the receiver table) over one batch of synthetic
+geometries: BASELINE config 3 -- 128-element array (+ centre element: E = 129),
+K = N = 905 launch rays / lens samples, 1024 x 1024 (r_outer, pipe_offset)
+grid per GPU.  With N GPUs the global grid is (1024 N) x 1024 radii x offsets
+and every rank owns a contiguous slice of radii (weak scaling, no collective
+on the data path: geometries are independent).
+
+`value`  : E*G_total / t with radius/offset resident in HBM (CUDA-event timed).
+`e2e`    : the same pass through the C ABI with HOST (pinned) buffers:
+           H2D of radius/offset and D2H of the table inside the timed region.
+`roofline`: FP64 instruction issue.  achieved = algorithmic FP64 ops of SURVEY
+           section 8(d) per launch / CUDA-event launch time; peak = FP64
+           instruction rate measured on this GPU by tofrt_measure_fp64_peak
+           (un-fused DMUL+DADD stream; MEASURED_PEAKS.json has no FP64 entry).
+`cpu_baseline`: the oracle port (C, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ray-solves/sec (element x pixel)"
+UNIT = "ray-solves/s"
+N_ELEM, K_RAYS, GRID_R, GRID_O = 128, 905, 1024, 1024
+
+
+def workload(rank, world, grid_r=GRID_R, grid_o=GRID_O):
+    from ray_tracing_ultrasound_b200 import reference_setup as rs
+    x_a, z_a = rs.transducer(num_elements=N_ELEM)
+    alpha, zf = rs.launch_angles(K_RAYS), rs.focus_line(K_RAYS)
+    radii, offsets = rs.synthetic_grid(grid_r * world, grid_o)
+    per = grid_r * grid_o
+    sl = slice(rank * per, (rank + 1) * per)
+    return x_a, z_a, alpha, zf, radii[sl], offsets[sl]
+
+
+def algorithmic_ops(G, K, N, E):
+    """W_g = K*(155 + 3N) + 2*E*K FP64 ops per geometry."""
+    return float(G) * (K * (155.0 + 3.0 * N) + 2.0 * E * K)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (profiling recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_port_rate(x_a, z_a, alpha, zf, radii, offsets, target_s=8.0):
+    """Oracle port (C, pthreads over geometries) on a bounded, evenly strided sample."""
+    from oracle.oracle import Oracle
+    o = Oracle(device_math=False)
+    p = o.params()
+    threads = o.max_threads()
+    n0 = min(len(radii), 64 * threads)
+    sel = np.linspace(0, len(radii) - 1, n0).astype(np.int64)
+    t0 = time.perf_counter()
+    o.table(p, radii[sel], offsets[sel], x_a[len(x_a) // 2], z_a[0], zf, alpha, x_a)
+    dt = time.perf_counter() - t0
+    n = int(min(len(radii), max(n0, n0 * target_s / max(dt, 1e-3))))
+    sel = np.linspace(0, len(radii) - 1, n).astype(np.int64)
+    t0 = time.perf_counter()
+    o.table(p, radii[sel], offsets[sel], x_a[len(x_a) // 2], z_a[0], zf, alpha, x_a)
+    dt = time.perf_counter() - t0
+    return len(x_a) * n / dt, threads, n, dt
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the reference is pure Python and cannot travel to the GPU box, so this arm
+    times the oracle port of the same path on all host threads (kind = "port")."""
+    if rank != 0:
+        return
+    x_a, z_a, alpha, zf, radii, offsets = workload(0, 1)
+    from oracle.oracle import Oracle
+    o = Oracle(device_math=False)
+    p = o.params()
+    threads = o.max_threads()
+    n = 256 * threads  # geometries per step: a bounded, evenly strided sample of the workload
+    sel = np.linspace(0, len(radii) - 1, n).astype(np.int64)
+    r_s, o_s = radii[sel], offsets[sel]
+    for _ in range(args.warmup):
+        o.table(p, r_s[: n // 8], o_s[: n // 8], x_a[64], z_a[64], zf, alpha, x_a)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.table(p, r_s, o_s, x_a[64], z_a[64], zf, alpha, x_a)
+    dt = time.perf_counter() - t0
+    value = len(x_a) * n * args.steps / dt
+    sample = f"{n} of {len(radii)} geometries per step, evenly strided, E={len(x_a)}, K=N={K_RAYS}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config 3: {N_ELEM}-element array, {GRID_R}x{GRID_O} geometry grid, K=N={K_RAYS}",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=GRID_R, help="radii per GPU (default 1024; offsets stay 1024)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ray_tracing_ultrasound_b200 import TofEngine, _build
+    if _build.is_stale():
+        _build.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    x_a, z_a, alpha, zf, radii, offsets = workload(rank, world, args.grid)
+    E, K, G = len(x_a), len(alpha), len(radii)
+    eng = TofEngine(local).setup(alpha, zf, x_a[N_ELEM // 2], z_a[N_ELEM // 2], x_a)
+    dev = torch.device("cuda", local)
+    r_d, o_d = torch.from_numpy(radii).to(dev), torch.from_numpy(offsets).to(dev)
+    tof_d = torch.empty((G, E), dtype=torch.float64, device=dev)
+    kh_d = torch.empty((G, E), dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        eng.tof_table_cuda(r_d, o_d, out_tof=tof_d, out_k_hit=kh_d)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    sampler.stop_flag = True
+    total_ms = ev[0].elapsed_time(ev[-1])
+    launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = E * G * world * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: C ABI with host (pinned) buffers, copies inside the timed region ----
+    r_h = torch.from_numpy(radii).pin_memory()
+    o_h = torch.from_numpy(offsets).pin_memory()
+    tof_h = torch.empty((G, E), dtype=torch.float64).pin_memory()
+    kh_h = torch.empty((G, E), dtype=torch.int32).pin_memory()
+    from ray_tracing_ultrasound_b200 import _capi
+
+    def e2e_step():
+        _capi.check(eng._lib.tofrt_table_host(eng._ctx, r_h.data_ptr(), o_h.data_ptr(), G, tof_h.data_ptr(),
+                                              kh_h.data_ptr(), None))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = E * G * world * e2e_steps / float(te.item())
+    parity_ok = bool(torch.equal(tof_h, tof_d.cpu()) and torch.equal(kh_h, kh_d.cpu()))
+
+    if rank == 0:
+        peak_fma, peak_issue = eng.measure_fp64_peak()
+        info = eng.kernel_info()
+        ops = algorithmic_ops(G, K, K, E)
+        kern_s = float(np.mean(launch_ms)) * 1e-3
+        roofline = {
+            "bound": "fp64-issue", "achieved": ops / kern_s / 1e12, "peak": peak_issue / 1e12, "unit": "TFLOP/s",
+            "frac": ops / kern_s / peak_issue, "traffic": None,
+            "peak_source": "tofrt_measure_fp64_peak on this GPU (un-fused DMUL+DADD thread-instructions/s); "
+                           "MEASURED_PEAKS.json holds no FP64 figure",
+            "peak_dfma_tflops": 2 * peak_fma / 1e12,
+            "kernel": "tofrt_table_kernel", "kernel_ms": kern_s * 1e3,
+            "algorithmic_ops_per_launch": ops,
+            "table_write_gbs": G * E * 12 / kern_s / 1e9,
+        }
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            roofline["hbm_peak_gbs_measured"] = peaks.get("hbm_gbs")
+        except Exception:
+            roofline["hbm_peak_gbs_measured"] = None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config 3: {N_ELEM}-element array (E={E}), K=N={K} rays/lens samples, "
+                                   f"{args.grid}x{GRID_O} (r_outer, pipe_offset) grid per GPU",
+                       "G_per_gpu": G, "E": E, "K": K, "parallelism": f"geometry-sharded x{world}",
+                       "l2": "outputs (1.6 GB per step) exceed L2; inputs are 16 MB + 60 KB of tables",
+                       "kernel": info},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(G * 16 * world),
+                    "d2h_bytes_per_step": int(G * E * 12 * world), "steps": e2e_steps,
+                    "matches_device_path": parity_ok},
+            "gpu_launches": args.steps * 1,
+            "roofline": roofline,
+        }
+        if not args.no_cpu:
+            v, threads, n, dt = cpu_port_rate(x_a, z_a, alpha, zf, radii, offsets)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": f"{n} of {G} geometries, evenly strided, {dt:.1f} s, oracle C port "
+                                             f"(glibc libm), E={E}, K=N={K}"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,106 @@
+/*
+ * tofrt.h -- C ABI of the B200-native time-of-flight ray-tracing engine.
+ *
+ * The reference (edudscrc/ray-tracing-ultrasound) has no FFI: its seam is the
+ * Python function shoot_rays() completed by module globals, plus the two
+ * script bodies.  Each entry point below names the reference code it replaces
+ * (file:line in /root/reference); INTEGRATION.md shows the ctypes binding a
+ * maintainer adds to main_rt.py / main_compare.py.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 or a negative TOFRT_E_*;
+ *     tofrt_last_error() gives the message (thread-local); nothing throws.
+ *   - geometric failures are data, not errors: a ray that misses the pipe or
+ *     the lens, or is totally reflected, is NaN in the ray records and simply
+ *     never matches a receiver (main_rt.py:392-393 stores None as NaN).
+ *   - "_dev" functions take device pointers and are asynchronous on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *     "_host" functions take host pointers, copy in/out and synchronise.
+ *   - table layout is geometry-major: tof[g*E + e], k_hit[g*E + e]; this is
+ *     the row order of database_2.csv (main_rt.py:464-504) and makes a
+ *     G-slice (one GPU's shard) one contiguous block.
+ */
+#ifndef TOFRT_H
+#define TOFRT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOFRT_VERSION 100
+
+#define TOFRT_OK 0
+#define TOFRT_E_BADARG (-1)   /* NULL pointer, negative size, mismatched lengths   */
+#define TOFRT_E_TOOFEW (-2)   /* < 2 lens samples: ValueError of main_rt.py:24-29  */
+#define TOFRT_E_CUDA (-3)     /* CUDA runtime error (message has the CUDA string)  */
+#define TOFRT_E_TOOLARGE (-4) /* K/E do not fit the 227 KB shared-memory staging   */
+#define TOFRT_E_NOSETUP (-5)  /* tofrt_setup() has not been called on this context */
+
+/* The module globals the reference's functions read (main_rt.py:449-455).
+ * d must be passed as the caller computed it (l0 + h0 in float64). */
+typedef struct tofrt_params {
+    double c1; /* speed of sound in the lens   (main_rt.py:449) */
+    double c2; /* speed of sound in the water  (main_rt.py:450) */
+    double l0; /* array-to-lens-apex distance  (main_rt.py:453) */
+    double h0; /* lens-apex-to-origin distance (main_rt.py:454) */
+    double d;  /* l0 + h0                      (main_rt.py:455) */
+} tofrt_params;
+
+/* Optional per-ray records of a trace, each [G][K] (NULL = not wanted).  These
+ * are the dict entries of shoot_rays (main_rt.py:432-441) that depend on the
+ * geometry, the discrete return-path index of main_rt.py:99, and the four
+ * travel-time legs of main_compare.py:514-517. */
+typedef struct tofrt_ray_records {
+    double *pipe_x, *pipe_z;   /* "pipe_x", "pipe_z"     */
+    double *lens2_x, *lens2_z; /* "lens_2_x", "lens_2_z" */
+    double *target_x;          /* "target_x" ("target_z" is a copy of z_f) */
+    int *idx;    /* >=0 first sign-change segment; -1 miss; <=-2: sample -2-idx on the line */
+    double *legs; /* [G][4][K] tof_1..tof_4 */
+} tofrt_ray_records;
+
+typedef struct tofrt_ctx tofrt_ctx;
+
+int tofrt_version(void);
+const char *tofrt_last_error(void);
+int tofrt_device_count(void);
+
+/* One context per (process, GPU).  Holds the lens tables and the staged setup. */
+int tofrt_create(tofrt_ctx **ctx, int device);
+int tofrt_destroy(tofrt_ctx *ctx);
+
+/* Replaces the per-iteration setup of main_rt.py:469-479 and the geometry-
+ * independent part of shoot_rays (main_rt.py:338-349): lens samples
+ * x_z_from_alpha(alpha), tangents, incident leg from the shooter
+ * (x_shooter, z_shooter) and the first refraction.  alpha, z_f: K host
+ * doubles (the reference's N lens samples are the same K angles).  x_rx: E
+ * receiver abscissae; rtol/atol: the np.isclose tolerances of
+ * main_rt.py:495 (1e-5, 1e-6) or main_compare.py:519 (1e-5, 1e-4). */
+int tofrt_setup(tofrt_ctx *ctx, const tofrt_params *params, const double *alpha, const double *z_f,
+                int K, double x_shooter, double z_shooter, const double *x_rx, int E, double rtol,
+                double atol);
+
+/* Lens samples of the current setup, "lens_1_x"/"lens_1_z" (main_rt.py:338). */
+int tofrt_lens_host(tofrt_ctx *ctx, double *lens_x, double *lens_z);
+
+/* Replaces the sweep body main_rt.py:464-501 for G geometries
+ * (radius[g], offset[g]) = (r_outer, pipe_offset): traces the K rays of the
+ * shot (shoot_rays, main_rt.py:351-405) and assembles, per receiver e, the
+ * first matching ray k_hit (-1: none) and tof_total (0.0 when not hit, as the
+ * CSV row keeps 0).  rec may be NULL. */
+int tofrt_table_dev(tofrt_ctx *ctx, const double *d_radius, const double *d_offset, long long G,
+                    double *d_tof, int *d_k_hit, const tofrt_ray_records *d_rec, void *stream);
+int tofrt_table_host(tofrt_ctx *ctx, const double *radius, const double *offset, long long G,
+                     double *tof, int *k_hit, const tofrt_ray_records *rec);
+
+/* Roofline denominator, measured on the device the context lives on: FP64
+ * instructions per second (thread-level) of a DFMA stream and of the un-fused
+ * DMUL+DADD stream the search loop issues (SURVEY.md section 8 d). */
+int tofrt_measure_fp64_peak(tofrt_ctx *ctx, double *dfma_per_s, double *dmul_dadd_per_s);
+
+/* Kernel-side facts for benchmarks/tests. */
+int tofrt_kernel_info(tofrt_ctx *ctx, int *grid, int *block, int *smem_bytes, int *regs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOFRT_H */

@@ -1,0 +1,45 @@
+"""Builds libtofrt.so (the C-ABI shared library) in-tree with nvcc for sm_100a."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtofrt.so")
+SOURCES = [os.path.join(HERE, "csrc", "tofrt_kernels.cu")]
+HEADERS = [os.path.join(HERE, "csrc", "tofrt_math.h"),
+           os.path.join(os.path.dirname(HERE), "include", "tofrt.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-fmad=false",  # NumPy never fuses mul+add; fused ops are explicit fma() only
+    "-Xcompiler", "-fPIC,-ffp-contract=off",
+    "-shared",
+]
+
+
+def nvcc_path():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libtofrt.so cannot be built")
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu -> libtofrt.so.  Cross-compiles without a GPU."""
+    if not force and not is_stale():
+        return LIB_PATH
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH

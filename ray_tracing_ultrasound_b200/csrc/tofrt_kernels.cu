@@ -1,0 +1,739 @@
+// tofrt_kernels.cu -- sm_100a kernels + C ABI of the TOF ray-tracing engine.
+//
+// What is computed is the reference's pulse-echo trace (main_rt.py:337-405) and
+// table assembly (main_rt.py:487-501); how it is computed is B200-first:
+//
+//   tofrt_prepare_kernel   geometry-independent work, once per setup: lens
+//                          samples, tangents, incident leg, first refraction
+//                          (main_rt.py:338-349) -> small tables in HBM/L2.
+//   tofrt_table_kernel     persistent grid (one CTA per SM).  The tables are
+//                          staged once per CTA in shared memory; every WARP
+//                          owns one geometry at a time (dynamic work counter),
+//                          walks its K rays 32 at a time with all per-ray state
+//                          in registers, and keeps the per-receiver first-hit
+//                          reduction warp-private in shared memory, so the
+//                          steady state has no block-level barrier at all.
+//                          The O(N) first-sign-change search of
+//                          find_line_curve_intersection (main_rt.py:78-99) is
+//                          the hot loop: broadcast LDS.128 of one lens sample,
+//                          DMUL+DADD+DADD (never fused: NumPy rounds twice),
+//                          and a 3-input integer min/max on the high words that
+//                          detects "sign change or exact zero in this chunk";
+//                          the warp leaves the loop when every lane has found
+//                          its chunk, and the exact index is resolved once
+//                          afterwards.
+//
+// Compile with -fmad=false: the only fused operations are the explicit fma()
+// calls inside tofrt_math.h (shared bit-for-bit with the oracle's twin build).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/tofrt.h"
+#include "tofrt_math.h"
+
+#define HALF_PI 1.5707963267948966 /* np.pi / 2 */
+
+namespace {
+
+constexpr int kThreads = 512;         // 16 warps per CTA, one CTA per SM
+constexpr int kWarps = kThreads / 32;
+constexpr int kChunk = 16;            // lens samples per early-exit check
+constexpr int kNoHit = 0x7fffffff;
+
+// Everything the kernels need that does not depend on the geometry.
+struct DevSetup {
+    // derived constants, computed on the host in the reference's operation order
+    double c1, c2, d;
+    double A, fourAC, twoA, twod, K2, phi1;  // lens surface (main_rt.py:181-212)
+    double c2_over_c1, c1_over_c2;           // v2 / v1 of the two refractions
+    double x_sh, z_sh;                       // shooter
+    double rtol, atol, tol_max;              // np.isclose tolerances, and an upper bound of atol+rtol|x_e|
+    double rx_min, rx_max;                   // finite receiver range
+    int K, Npad, E, E_sorted, has_nonfinite_rx, tables_ok;
+    // tables in global memory
+    const double2 *lens;   // [Npad] (x_p, z_p), padded with copies of the last sample
+    const double *a_pq, *b_pq, *phi_pq, *z_f, *leg1;  // [K]
+    const double *x_rx;    // [E] as given
+    const double *xs;      // [E_sorted] finite receivers, ascending
+    const int *perm;       // [E_sorted] original index of xs[i]
+};
+
+struct TableArgs {
+    const double *radius, *offset;
+    long long G;
+    double *tof;
+    int *k_hit;
+    tofrt_ray_records rec;
+    unsigned long long *counter;
+};
+
+// ---- small device helpers ---------------------------------------------------
+
+__device__ __forceinline__ unsigned hi32(double v) { return (unsigned)__double2hiint(v); }
+
+// np.sign class: 0 negative, 1 zero, 2 positive, 3 NaN
+__device__ __forceinline__ int sign_class(double v) { return v > 0 ? 2 : (v < 0 ? 0 : (v == 0 ? 1 : 3)); }
+// np.diff(np.sign(d)) != 0 (NaN - x is NaN and NaN != 0 is True)
+__device__ __forceinline__ bool class_change(int c0, int c1) { return c0 == 3 || c1 == 3 || c0 != c1; }
+
+// np.isclose(a, b, rtol, atol)
+__device__ __forceinline__ bool np_isclose(double a, double b, double rtol, double atol)
+{
+    return ((fabs(a - b) <= atol + rtol * fabs(b)) && isfinite(b)) || (a == b);
+}
+// Python min/max on two floats
+__device__ __forceinline__ double py_min(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double py_max(double a, double b) { return (b > a) ? b : a; }
+
+__device__ __forceinline__ double dist2d(double x1, double z1, double x2, double z2)
+{
+    return sqrt((x1 - x2) * (x1 - x2) + (z1 - z2) * (z1 - z2));
+}
+
+// vertical difference of main_rt.py:78-79, two roundings
+__device__ __forceinline__ double line_diff(double2 s, double m, double b) { return s.y - (m * s.x + b); }
+
+// h(alpha), dz/dalpha, dx/dalpha (main_rt.py:180-234); B of :184 and :203 are the same bits
+__device__ __forceinline__ void lens_point(const DevSetup &S, double sn, double cs, double *h, double *dz,
+                                           double *dx)
+{
+    double B = S.twod * cs - S.K2;
+    double sd = sqrt(B * B - S.fourAC);
+    double hh = (-B - sd) / S.twoA;
+    double dB = -S.twod * sn;
+    double dB2 = 2 * B * dB;
+    double dS = (1 / (2 * sd)) * dB2;
+    double dh = S.phi1 * (dB + dS);
+    *h = hh;
+    *dz = dh * cs - hh * sn;
+    *dx = dh * sn + hh * cs;
+}
+
+// refraction of main_rt.py:267-280 with the tuple form of dzdx
+__device__ __forceinline__ double refract(double phi_in, double dz, double dx, double v2_over_v1)
+{
+    double phi_slope = tofrt_atan2(dz, dx);
+    double theta_1 = phi_in - (phi_slope + HALF_PI);
+    double theta_2 = tofrt_asin(v2_over_v1 * tofrt_sin(theta_1));
+    return phi_slope - HALF_PI + theta_2;
+}
+
+// ---- prepare kernel: main_rt.py:338-349 for every launch angle ----------------
+__global__ void tofrt_prepare_kernel(DevSetup S, const double *alpha, double2 *lens, double *a_pq,
+                                     double *b_pq, double *phi_pq, double *leg1, int *bad)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= S.Npad) return;
+    int kk = k < S.K ? k : S.K - 1;  // padding repeats the last sample
+    double al = alpha[kk];
+    double sn, cs, h, dz, dx;
+    tofrt_sincos(al, &sn, &cs);
+    lens_point(S, sn, cs, &h, &dz, &dx);
+    double x_p = h * sn, z_p = h * cs;
+    lens[k] = make_double2(x_p, z_p);
+    if (k >= S.K) return;
+    if (!(fabs(x_p) < 1e150 && fabs(z_p) < 1e150)) atomicOr(bad, 1);
+    double phi_ap = tofrt_atan2(S.z_sh - z_p, S.x_sh - x_p);
+    double phi = refract(phi_ap, dz, dx, S.c2_over_c1);
+    double a = tofrt_tan(phi);
+    a_pq[k] = a;
+    b_pq[k] = z_p - a * x_p;
+    phi_pq[k] = phi;
+    leg1[k] = dist2d(S.x_sh, S.z_sh, x_p, z_p) / S.c1;
+}
+
+// ---- exact (slow) pieces of find_line_curve_intersection ------------------------
+
+// first j in [j0, N-2] with a sign-class change between samples j and j+1, else -1
+__device__ __noinline__ int scan_exact_from(const double2 *lens, int N, double m, double b, int j0)
+{
+    int cprev = sign_class(line_diff(lens[j0], m, b));
+    for (int j = j0; j + 1 < N; ++j) {
+        int cnext = sign_class(line_diff(lens[j + 1], m, b));
+        if (class_change(cprev, cnext)) return j;
+        cprev = cnext;
+    }
+    return -1;
+}
+
+// main_rt.py:106-168: intersect the line with chord (idx, idx+1)
+__device__ __forceinline__ void chord_intersection(const double2 *lens, int idx, double m, double b, double *xi,
+                                                   double *zi)
+{
+    double2 p1 = lens[idx], p2 = lens[idx + 1];
+    double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
+    double rx = NAN, ry = NAN;
+    if (np_isclose(x1, x2, 1e-5, 1e-8)) {  // :110-123 vertical chord
+        double y_int = m * x1 + b;
+        if (y_int >= py_min(y1, y2) - 1e-9 && y_int <= py_max(y1, y2) + 1e-9) { rx = x1; ry = y_int; }
+    } else {
+        double m_seg = (y2 - y1) / (x2 - x1);
+        double b_seg = y1 - m_seg * x1;
+        if (np_isclose(m, m_seg, 1e-5, 1e-8)) {  // :131-144 parallel
+            if (np_isclose(b, b_seg, 1e-5, 1e-8)) { rx = (x1 + x2) / 2.0; ry = m * rx + b; }
+        } else {  // :147-168
+            double x_int = (b_seg - b) / (m - m_seg);
+            double y_int = m * x_int + b;
+            if (x_int >= py_min(x1, x2) - 1e-9 && x_int <= py_max(x1, x2) + 1e-9 &&
+                y_int >= py_min(y1, y2) - 1e-9 && y_int <= py_max(y1, y2) + 1e-9) {
+                rx = x_int; ry = y_int;
+            }
+        }
+    }
+    *xi = rx; *zi = ry;
+}
+
+// ---- the table kernel -----------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, TableArgs T)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = S.K, N = S.K, Npad = S.Npad, E = S.E;
+    // shared-memory carve-up
+    double2 *s_lens = reinterpret_cast<double2 *>(smem_raw);
+    double *s_a = reinterpret_cast<double *>(s_lens + Npad);
+    double *s_b = s_a + K;
+    double *s_phi = s_b + K;
+    double *s_zf = s_phi + K;
+    double *s_xs = s_zf + K;
+    double *s_tof = s_xs + S.E_sorted;               // [kWarps][E]
+    int *s_perm = reinterpret_cast<int *>(s_tof + (size_t)kWarps * E);
+    int *s_khit = s_perm + S.E_sorted;               // [kWarps][E]
+
+    for (int i = threadIdx.x; i < Npad; i += kThreads) s_lens[i] = S.lens[i];
+    for (int i = threadIdx.x; i < K; i += kThreads) {
+        s_a[i] = S.a_pq[i]; s_b[i] = S.b_pq[i]; s_phi[i] = S.phi_pq[i]; s_zf[i] = S.z_f[i];
+    }
+    for (int i = threadIdx.x; i < S.E_sorted; i += kThreads) { s_xs[i] = S.xs[i]; s_perm[i] = S.perm[i]; }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *w_tof = s_tof + (size_t)warp * E;
+    int *w_khit = s_khit + (size_t)warp * E;
+    const int nchunks = (K + 31) >> 5;
+    const unsigned FULL = 0xffffffffu;
+
+    for (;;) {
+        unsigned long long g64 = 0;
+        if (lane == 0) g64 = atomicAdd(T.counter, 1ull);
+        g64 = __shfl_sync(FULL, g64, 0);
+        if (g64 >= (unsigned long long)T.G) break;
+        const long long g = (long long)g64;
+        const double r_outer = T.radius[g], pipe_offset = T.offset[g];
+        const double rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset;
+        for (int e = lane; e < E; e += 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0; }
+        __syncwarp();
+
+        for (int c = 0; c < nchunks; ++c) {
+            const int k = (c << 5) + lane;
+            const bool valid = k < K;
+            const int kk = valid ? k : K - 1;
+            const double a_pq = s_a[kk], b_pq = s_b[kk], phi_pq = s_phi[kk];
+
+            // ---- main_rt.py:351-364 pipe intersection, upper root ----
+            double x_q, z_q;
+            {
+                double A2 = a_pq * a_pq + 1;
+                double B2 = 2 * (a_pq * b_pq - pipe_offset);
+                double C2 = offsq + b_pq * b_pq - rsq;
+                double sd = sqrt(B2 * B2 - 4 * A2 * C2);
+                double den = 2 * A2;
+                double x_q1 = (-B2 + sd) / den, x_q2 = (-B2 - sd) / den;
+                double z_q1 = a_pq * x_q1 + b_pq, z_q2 = a_pq * x_q2 + b_pq;
+                bool up = z_q1 > z_q2;
+                x_q = up ? x_q1 : x_q2;
+                z_q = up ? z_q1 : z_q2;
+            }
+            // ---- main_rt.py:367-376 reflection on the pipe ----
+            double phi_l, m, b;
+            {
+                double slope = -x_q / sqrt(rsq - x_q * x_q);  // dzdx_pipe ignores the offset (:237-238)
+                double phi_slope = tofrt_atan(slope);
+                double theta_1 = phi_pq - (phi_slope + HALF_PI);
+                phi_l = phi_slope - HALF_PI + (-theta_1);
+                m = tofrt_tan(phi_l);
+                b = z_q - m * x_q;
+            }
+
+            // ---- main_rt.py:78-99 first sign change over the sampled lens ----
+            // fast path precondition: every diff is finite, so only {-,0,+} occur
+            const bool fast = valid && S.tables_ok && fabs(m) < 1e150 && fabs(b) < 1e150;
+            int flagged = -1;
+            {
+                unsigned hp = hi32(line_diff(s_lens[0], m, b));
+                for (int base = 1; base < Npad; base += kChunk) {
+                    unsigned mn = hp, mx = hp;
+#pragma unroll
+                    for (int u = 0; u < kChunk; u += 2) {
+                        unsigned ha = hi32(line_diff(s_lens[base + u], m, b));
+                        unsigned hb = hi32(line_diff(s_lens[base + u + 1], m, b));
+                        mn = __vimin3_u32(mn, ha, hb);
+                        mx = __vimax3_u32(mx, ha, hb);
+                        hp = hb;
+                    }
+                    // sign differs inside the chunk, or a +-0 (high word 0 / 0x80000000) occurred
+                    bool flag = ((int)(mn ^ mx) < 0) || ((mn << 1) == 0u);
+                    if (flag && flagged < 0) flagged = base;
+                    if (__all_sync(FULL, flagged >= 0 || !fast)) break;
+                }
+            }
+            int idx = -1;  // >= 0 segment, -1 none
+            if (valid) {
+                if (!fast) {
+                    idx = scan_exact_from(s_lens, N, m, b, 0);
+                } else if (flagged >= 0) {
+                    // resolve the exact index inside the flagged chunk (samples flagged-1 .. flagged+kChunk-1)
+                    int j0 = flagged - 1;
+                    int jend = min(flagged + kChunk - 1, N - 1);
+                    int cprev = sign_class(line_diff(s_lens[j0], m, b));
+                    for (int j = j0; j < jend; ++j) {
+                        int cnext = sign_class(line_diff(s_lens[j + 1], m, b));
+                        if (class_change(cprev, cnext)) { idx = j; break; }
+                        cprev = cnext;
+                    }
+                    // conservative flag without a real change (a denormal diff): keep going exactly
+                    if (idx < 0 && jend < N - 1) idx = scan_exact_from(s_lens, N, m, b, jend);
+                }
+            }
+            // ---- main_rt.py:84-96 no crossing: is a sample on the line (|diff| <= 1e-8)? ----
+            // warp-cooperative: the 32 lanes test 32 consecutive samples of one ray at a time
+            int on_sample = -1;
+            {
+                unsigned need = __ballot_sync(FULL, valid && idx < 0);
+                while (need) {
+                    int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    double mm = __shfl_sync(FULL, m, src), bb = __shfl_sync(FULL, b, src);
+                    int first = kNoHit;
+                    for (int j = lane; j < N; j += 32) {
+                        double dd = line_diff(s_lens[j], mm, bb);
+                        if (fabs(dd) <= 1e-8) { first = j; break; }
+                    }
+                    first = __reduce_min_sync(FULL, first);
+                    if (lane == src && first != kNoHit) on_sample = first;
+                }
+            }
+            double ix = NAN, iz = NAN;
+            if (idx >= 0) chord_intersection(s_lens, idx, m, b, &ix, &iz);
+            else if (on_sample >= 0) { double2 s = s_lens[on_sample]; ix = s.x; iz = s.y; }
+
+            // ---- main_rt.py:396-405 refraction back into the lens, landing point ----
+            double target_x;
+            {
+                double alpha_i = tofrt_atan2(ix, iz);
+                double sn, cs, h, dz, dx;
+                tofrt_sincos(alpha_i, &sn, &cs);
+                lens_point(S, sn, cs, &h, &dz, &dx);
+                double phi_last = refract(phi_l, dz, dx, S.c1_over_c2);
+                double a_i = tofrt_tan(phi_last);
+                double b_i = iz - a_i * ix;
+                target_x = (s_zf[kk] - b_i) / a_i;
+            }
+
+            // ---- optional per-ray records ----
+            if (valid) {
+                size_t o = (size_t)g * K + k;
+                if (T.rec.pipe_x) T.rec.pipe_x[o] = x_q;
+                if (T.rec.pipe_z) T.rec.pipe_z[o] = z_q;
+                if (T.rec.lens2_x) T.rec.lens2_x[o] = ix;
+                if (T.rec.lens2_z) T.rec.lens2_z[o] = iz;
+                if (T.rec.target_x) T.rec.target_x[o] = target_x;
+                if (T.rec.idx) T.rec.idx[o] = idx >= 0 ? idx : (on_sample >= 0 ? -2 - on_sample : -1);
+            }
+
+            // ---- main_rt.py:487-501 which receivers does this ray land on? ----
+            // candidates: finite receivers within tol_max of target_x (binary search in the
+            // sorted copy); the exact np.isclose decides.  +-inf landing points can only match
+            // an identical infinite receiver.
+            bool cand = valid && target_x >= S.rx_min - S.tol_max && target_x <= S.rx_max + S.tol_max;
+            bool special = valid && S.has_nonfinite_rx && isinf(target_x);
+            const bool want_legs = T.rec.legs != nullptr;
+            if (__any_sync(FULL, cand || special || want_legs)) {
+                int lo = 0, hi = 0;
+                bool mine = false;
+                if (cand) {
+                    double tl = target_x - S.tol_max, th = target_x + S.tol_max;
+                    int l = 0, r = S.E_sorted;
+                    while (l < r) { int mid = (l + r) >> 1; if (s_xs[mid] < tl) l = mid + 1; else r = mid; }
+                    lo = l;
+                    hi = l;
+                    while (hi < S.E_sorted && s_xs[hi] <= th) ++hi;
+                    for (int i = lo; i < hi; ++i)
+                        if (np_isclose(target_x, s_xs[i], S.rtol, S.atol)) { atomicMin(&w_khit[s_perm[i]], k); mine = true; }
+                }
+                if (special) {
+                    for (int e = 0; e < E; ++e)
+                        if (target_x == S.x_rx[e]) { atomicMin(&w_khit[e], k); mine = true; }
+                }
+                __syncwarp();
+                if (mine || (want_legs && valid)) {
+                    // main_rt.py:497-500 / main_compare.py:514-517
+                    double2 p = s_lens[kk];
+                    double t1 = S.leg1[kk];
+                    double t2 = dist2d(p.x, p.y, x_q, z_q) / S.c2;
+                    double t3 = dist2d(x_q, z_q, ix, iz) / S.c2;
+                    double t4 = dist2d(ix, iz, target_x, s_zf[kk]) / S.c1;
+                    if (want_legs) {
+                        size_t o = (size_t)g * 4 * K + k;
+                        T.rec.legs[o] = t1; T.rec.legs[o + K] = t2;
+                        T.rec.legs[o + 2 * (size_t)K] = t3; T.rec.legs[o + 3 * (size_t)K] = t4;
+                    }
+                    if (mine) {
+                        double tof = t1;
+                        tof += t2;
+                        tof += t3;
+                        tof += t4;
+                        for (int i = lo; i < hi; ++i) {
+                            int e = s_perm[i];
+                            if (w_khit[e] == k) w_tof[e] = tof;
+                        }
+                        if (special)
+                            for (int e = 0; e < E; ++e)
+                                if (w_khit[e] == k) w_tof[e] = tof;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ---- one geometry done: coalesced row of the [G][E] table ----
+        __syncwarp();
+        for (int e = lane; e < E; e += 32) {
+            int kh = w_khit[e];
+            T.tof[(size_t)g * E + e] = w_tof[e];
+            T.k_hit[(size_t)g * E + e] = kh == kNoHit ? -1 : kh;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- FP64 issue-rate micro-benchmark (the roofline denominator, measured on the box) ----
+// 8 independent dependency chains per thread; MODE 0: DFMA, MODE 1: DMUL+DADD (un-fused, as
+// the scan issues them).  Each loop iteration issues 16 FP64 instructions per thread.
+template <int MODE>
+__global__ void __launch_bounds__(256) tofrt_fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (double)(threadIdx.x + i) * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (MODE == 0) { v[i] = fma(v[i], a, b); v[i] = fma(v[i], a, b); }
+            else { v[i] = __dmul_rn(v[i], a); v[i] = __dadd_rn(v[i], b); }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
+
+// ---- host side ----------------------------------------------------------------------
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(TOFRT_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+}  // namespace
+
+struct tofrt_ctx {
+    int device = 0;
+    int sm_count = 0;
+    bool ready = false;
+    DevSetup S{};
+    int K = 0, E = 0;
+    size_t smem = 0;
+    // device buffers owned by the context
+    double *d_alpha = nullptr, *d_zf = nullptr, *d_a = nullptr, *d_b = nullptr, *d_phi = nullptr, *d_leg1 = nullptr;
+    double2 *d_lens = nullptr;
+    double *d_xrx = nullptr, *d_xs = nullptr;
+    int *d_perm = nullptr, *d_bad = nullptr;
+    unsigned long long *d_counter = nullptr;
+    void free_all()
+    {
+        cudaFree(d_alpha); cudaFree(d_zf); cudaFree(d_a); cudaFree(d_b); cudaFree(d_phi); cudaFree(d_leg1);
+        cudaFree(d_lens); cudaFree(d_xrx); cudaFree(d_xs); cudaFree(d_perm); cudaFree(d_bad);
+        d_alpha = d_zf = d_a = d_b = d_phi = d_leg1 = d_xrx = d_xs = nullptr;
+        d_lens = nullptr; d_perm = d_bad = nullptr;
+    }
+};
+
+extern "C" {
+
+int tofrt_version(void) { return TOFRT_VERSION; }
+const char *tofrt_last_error(void) { return g_err.c_str(); }
+
+int tofrt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tofrt_create(tofrt_ctx **out, int device)
+{
+    if (!out) return fail(TOFRT_E_BADARG, "tofrt_create: ctx is NULL");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(device));
+    tofrt_ctx *c = new tofrt_ctx();
+    c->device = device;
+    cudaError_t e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_bad, sizeof(int));
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(TOFRT_E_CUDA, std::string("tofrt_create: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return TOFRT_OK;
+}
+
+int tofrt_destroy(tofrt_ctx *c)
+{
+    if (!c) return TOFRT_OK;
+    cudaSetDevice(c->device);
+    c->free_all();
+    cudaFree(c->d_counter);
+    delete c;
+    return TOFRT_OK;
+}
+
+int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const double *z_f, int K,
+                double x_shooter, double z_shooter, const double *x_rx, int E, double rtol, double atol)
+{
+    if (!c || !p || !alpha || !z_f || !x_rx) return fail(TOFRT_E_BADARG, "tofrt_setup: NULL argument");
+    if (K < 2) return fail(TOFRT_E_TOOFEW, "Curve needs at least two points.");
+    if (E < 1) return fail(TOFRT_E_BADARG, "tofrt_setup: need at least one receiver");
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->ready = false;
+    c->free_all();
+    CUDA_TRY(cudaMalloc(&c->d_bad, sizeof(int)));
+
+    DevSetup S{};
+    S.c1 = p->c1; S.c2 = p->c2; S.d = p->d;
+    // main_rt.py:181-185 and :199-201, same operation order as NumPy
+    const double T = p->l0 / p->c1 + p->h0 / p->c2;
+    const double c1sq = p->c1 * p->c1, c2sq = p->c2 * p->c2;
+    S.A = (c1sq / c2sq) - 1;
+    const double C = (c1sq * (T * T)) - (p->d * p->d);
+    S.fourAC = 4 * S.A * C;
+    S.twoA = 2 * S.A;
+    S.twod = 2 * p->d;
+    S.K2 = 2 * T * c1sq / p->c2;
+    S.phi1 = -1 / (2 * S.A);
+    S.c2_over_c1 = p->c2 / p->c1;
+    S.c1_over_c2 = p->c1 / p->c2;
+    S.x_sh = x_shooter; S.z_sh = z_shooter;
+    S.rtol = rtol; S.atol = atol;
+    S.K = K; S.E = E;
+    S.Npad = 1 + ((K - 1 + kChunk - 1) / kChunk) * kChunk;
+
+    // receivers: sorted finite copy for the candidate search
+    std::vector<int> order;
+    double amax = 0.0;
+    int nonfinite = 0;
+    for (int e = 0; e < E; ++e) {
+        if (std::isfinite(x_rx[e])) { order.push_back(e); amax = std::max(amax, std::fabs(x_rx[e])); }
+        else nonfinite = 1;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int i, int j) { return x_rx[i] < x_rx[j]; });
+    std::vector<double> xs(order.size());
+    for (size_t i = 0; i < order.size(); ++i) xs[i] = x_rx[order[i]];
+    S.E_sorted = (int)order.size();
+    S.has_nonfinite_rx = nonfinite;
+    // upper bound of atol + rtol*|x_e| with slack for the rounding of target_x -+ tol_max
+    S.tol_max = (std::fabs(atol) + std::fabs(rtol) * amax) * 1.0000001 + 1e-300;
+    if (!std::isfinite(S.tol_max)) S.tol_max = 1.7e308;
+    S.rx_min = xs.empty() ? 1.0 : xs.front();
+    S.rx_max = xs.empty() ? -1.0 : xs.back();
+
+    const size_t smem = (size_t)S.Npad * sizeof(double2) + (size_t)K * 4 * sizeof(double) +
+                        (size_t)S.E_sorted * (sizeof(double) + sizeof(int)) +
+                        (size_t)kWarps * E * (sizeof(double) + sizeof(int)) + 16;
+    if (smem > 227 * 1024)
+        return fail(TOFRT_E_TOOLARGE, "tofrt_setup: K/E need " + std::to_string(smem) + " B of shared memory (> 227 KB)");
+
+    CUDA_TRY(cudaMalloc(&c->d_alpha, sizeof(double) * K));
+    CUDA_TRY(cudaMalloc(&c->d_zf, sizeof(double) * K));
+    CUDA_TRY(cudaMalloc(&c->d_a, sizeof(double) * K));
+    CUDA_TRY(cudaMalloc(&c->d_b, sizeof(double) * K));
+    CUDA_TRY(cudaMalloc(&c->d_phi, sizeof(double) * K));
+    CUDA_TRY(cudaMalloc(&c->d_leg1, sizeof(double) * K));
+    CUDA_TRY(cudaMalloc(&c->d_lens, sizeof(double2) * S.Npad));
+    CUDA_TRY(cudaMalloc(&c->d_xrx, sizeof(double) * E));
+    CUDA_TRY(cudaMalloc(&c->d_xs, sizeof(double) * std::max(1, S.E_sorted)));
+    CUDA_TRY(cudaMalloc(&c->d_perm, sizeof(int) * std::max(1, S.E_sorted)));
+    CUDA_TRY(cudaMemcpy(c->d_alpha, alpha, sizeof(double) * K, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->d_zf, z_f, sizeof(double) * K, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->d_xrx, x_rx, sizeof(double) * E, cudaMemcpyHostToDevice));
+    if (S.E_sorted) {
+        CUDA_TRY(cudaMemcpy(c->d_xs, xs.data(), sizeof(double) * S.E_sorted, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(c->d_perm, order.data(), sizeof(int) * S.E_sorted, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemset(c->d_bad, 0, sizeof(int)));
+    S.lens = c->d_lens; S.a_pq = c->d_a; S.b_pq = c->d_b; S.phi_pq = c->d_phi; S.z_f = c->d_zf;
+    S.leg1 = c->d_leg1; S.x_rx = c->d_xrx; S.xs = c->d_xs; S.perm = c->d_perm;
+
+    tofrt_prepare_kernel<<<(S.Npad + 127) / 128, 128>>>(S, c->d_alpha, c->d_lens, c->d_a, c->d_b, c->d_phi,
+                                                        c->d_leg1, c->d_bad);
+    CUDA_TRY(cudaGetLastError());
+    int bad = 0;
+    CUDA_TRY(cudaMemcpy(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    S.tables_ok = bad ? 0 : 1;
+
+    CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c->S = S; c->K = K; c->E = E; c->smem = smem;
+    c->ready = true;
+    return TOFRT_OK;
+}
+
+int tofrt_lens_host(tofrt_ctx *c, double *lens_x, double *lens_z)
+{
+    if (!c || !lens_x || !lens_z) return fail(TOFRT_E_BADARG, "tofrt_lens_host: NULL argument");
+    if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_lens_host: call tofrt_setup first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<double2> h(c->K);
+    CUDA_TRY(cudaMemcpy(h.data(), c->d_lens, sizeof(double2) * c->K, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < c->K; ++k) { lens_x[k] = h[k].x; lens_z[k] = h[k].y; }
+    return TOFRT_OK;
+}
+
+int tofrt_table_dev(tofrt_ctx *c, const double *d_radius, const double *d_offset, long long G, double *d_tof,
+                    int *d_k_hit, const tofrt_ray_records *d_rec, void *stream)
+{
+    if (!c || G < 0) return fail(TOFRT_E_BADARG, "tofrt_table_dev: bad argument");
+    if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_table_dev: call tofrt_setup first");
+    if (G == 0) return TOFRT_OK;
+    if (!d_radius || !d_offset || !d_tof || !d_k_hit) return fail(TOFRT_E_BADARG, "tofrt_table_dev: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TableArgs T{};
+    T.radius = d_radius; T.offset = d_offset; T.G = G; T.tof = d_tof; T.k_hit = d_k_hit;
+    if (d_rec) T.rec = *d_rec;
+    T.counter = c->d_counter;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+    long long warps_needed = G;
+    int grid = (int)std::min<long long>(c->sm_count, (warps_needed + kWarps - 1) / kWarps);
+    tofrt_table_kernel<<<grid, kThreads, c->smem, st>>>(c->S, T);
+    CUDA_TRY(cudaGetLastError());
+    return TOFRT_OK;
+}
+
+int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, long long G, double *tof,
+                     int *k_hit, const tofrt_ray_records *rec)
+{
+    if (!c || G < 0) return fail(TOFRT_E_BADARG, "tofrt_table_host: bad argument");
+    if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_table_host: call tofrt_setup first");
+    if (G == 0) return TOFRT_OK;
+    if (!radius || !offset || !tof || !k_hit) return fail(TOFRT_E_BADARG, "tofrt_table_host: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t K = c->K, E = c->E, g = (size_t)G;
+    double *d_in = nullptr, *d_tof = nullptr;
+    int *d_kh = nullptr;
+    std::vector<void *> owned;
+    auto cleanup = [&]() { for (void *q : owned) cudaFree(q); };
+    auto dalloc = [&](void **q, size_t bytes) {
+        cudaError_t e = cudaMalloc(q, bytes);
+        if (e == cudaSuccess) owned.push_back(*q);
+        return e;
+    };
+#define TRY_C(expr)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) { cleanup(); return fail(TOFRT_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } \
+    } while (0)
+    TRY_C(dalloc((void **)&d_in, sizeof(double) * 2 * g));
+    TRY_C(dalloc((void **)&d_tof, sizeof(double) * g * E));
+    TRY_C(dalloc((void **)&d_kh, sizeof(int) * g * E));
+    TRY_C(cudaMemcpy(d_in, radius, sizeof(double) * g, cudaMemcpyHostToDevice));
+    TRY_C(cudaMemcpy(d_in + g, offset, sizeof(double) * g, cudaMemcpyHostToDevice));
+    tofrt_ray_records drec{};
+    if (rec) {
+        if (rec->pipe_x) TRY_C(dalloc((void **)&drec.pipe_x, sizeof(double) * g * K));
+        if (rec->pipe_z) TRY_C(dalloc((void **)&drec.pipe_z, sizeof(double) * g * K));
+        if (rec->lens2_x) TRY_C(dalloc((void **)&drec.lens2_x, sizeof(double) * g * K));
+        if (rec->lens2_z) TRY_C(dalloc((void **)&drec.lens2_z, sizeof(double) * g * K));
+        if (rec->target_x) TRY_C(dalloc((void **)&drec.target_x, sizeof(double) * g * K));
+        if (rec->idx) TRY_C(dalloc((void **)&drec.idx, sizeof(int) * g * K));
+        if (rec->legs) TRY_C(dalloc((void **)&drec.legs, sizeof(double) * g * K * 4));
+    }
+    int rc = tofrt_table_dev(c, d_in, d_in + g, G, d_tof, d_kh, rec ? &drec : nullptr, nullptr);
+    if (rc != TOFRT_OK) { cleanup(); return rc; }
+    TRY_C(cudaMemcpy(tof, d_tof, sizeof(double) * g * E, cudaMemcpyDeviceToHost));
+    TRY_C(cudaMemcpy(k_hit, d_kh, sizeof(int) * g * E, cudaMemcpyDeviceToHost));
+    if (rec) {
+        if (rec->pipe_x) TRY_C(cudaMemcpy(rec->pipe_x, drec.pipe_x, sizeof(double) * g * K, cudaMemcpyDeviceToHost));
+        if (rec->pipe_z) TRY_C(cudaMemcpy(rec->pipe_z, drec.pipe_z, sizeof(double) * g * K, cudaMemcpyDeviceToHost));
+        if (rec->lens2_x) TRY_C(cudaMemcpy(rec->lens2_x, drec.lens2_x, sizeof(double) * g * K, cudaMemcpyDeviceToHost));
+        if (rec->lens2_z) TRY_C(cudaMemcpy(rec->lens2_z, drec.lens2_z, sizeof(double) * g * K, cudaMemcpyDeviceToHost));
+        if (rec->target_x) TRY_C(cudaMemcpy(rec->target_x, drec.target_x, sizeof(double) * g * K, cudaMemcpyDeviceToHost));
+        if (rec->idx) TRY_C(cudaMemcpy(rec->idx, drec.idx, sizeof(int) * g * K, cudaMemcpyDeviceToHost));
+        if (rec->legs) TRY_C(cudaMemcpy(rec->legs, drec.legs, sizeof(double) * g * K * 4, cudaMemcpyDeviceToHost));
+    }
+    TRY_C(cudaDeviceSynchronize());
+    cleanup();
+#undef TRY_C
+    return TOFRT_OK;
+}
+
+int tofrt_measure_fp64_peak(tofrt_ctx *c, double *dfma_per_s, double *dmul_dadd_per_s)
+{
+    if (!c || !dfma_per_s || !dmul_dadd_per_s) return fail(TOFRT_E_BADARG, "tofrt_measure_fp64_peak: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    double *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 1 << 14, blocks = c->sm_count * 8, threads = 256;
+    const double inst = (double)blocks * threads * iters * 16.0;
+    double best[2] = {0, 0};
+    for (int mode = 0; mode < 2; ++mode) {
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(e0);
+            if (mode == 0) tofrt_fp64_peak_kernel<0><<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);
+            else tofrt_fp64_peak_kernel<1><<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);
+            cudaEventRecord(e1);
+            cudaError_t e = cudaEventSynchronize(e1);
+            if (e != cudaSuccess) { cudaFree(d_out); return fail(TOFRT_E_CUDA, cudaGetErrorString(e)); }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0) best[mode] = std::max(best[mode], inst / (ms * 1e-3));
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *dfma_per_s = best[0];
+    *dmul_dadd_per_s = best[1];
+    return TOFRT_OK;
+}
+
+int tofrt_kernel_info(tofrt_ctx *c, int *grid, int *block, int *smem_bytes, int *regs)
+{
+    if (!c) return fail(TOFRT_E_BADARG, "tofrt_kernel_info: ctx is NULL");
+    cudaFuncAttributes fa{};
+    CUDA_TRY(cudaFuncGetAttributes(&fa, tofrt_table_kernel));
+    if (grid) *grid = c->sm_count;
+    if (block) *block = kThreads;
+    if (smem_bytes) *smem_bytes = (int)c->smem;
+    if (regs) *regs = fa.numRegs;
+    return TOFRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+"""Host-side mirror of the reference's hot path over the C ABI (include/tofrt.h).
+
+`TofEngine` = one tofrt context (one GPU).  `setup()` plays the role of the
+per-iteration setup of main_rt.py:469-479 plus the module globals
+(main_rt.py:449-462); `tof_table()` is the sweep body main_rt.py:464-501 for a
+batch of geometries; `shoot_rays()` returns the dict of main_rt.py:432-441.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from . import reference_setup as rs
+
+RECORD_KEYS = ("pipe_x", "pipe_z", "lens2_x", "lens2_z", "target_x", "idx", "legs")
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class TofTable:
+    """Element x geometry table, geometry-major: tof[g, e], k_hit[g, e]."""
+
+    def __init__(self, tof, k_hit, records=None):
+        self.tof = tof
+        self.k_hit = k_hit
+        self.records = records or {}
+
+    @property
+    def hit(self):
+        return self.k_hit >= 0
+
+
+class TofEngine:
+    def __init__(self, device=0):
+        self._lib = _capi.load()
+        if self._lib.tofrt_device_count() <= device:
+            raise RuntimeError(f"CUDA device {device} not available (the engine has no CPU fallback)")
+        self._ctx = ctypes.c_void_p()
+        _capi.check(self._lib.tofrt_create(ctypes.byref(self._ctx), int(device)))
+        self.device = int(device)
+        self.K = self.E = 0
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.tofrt_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- main_rt.py:449-479 -------------------------------------------------
+    def setup(self, alpha, z_f, x_shooter, z_shooter, x_rx, c1=rs.C1, c2=rs.C2, l0=rs.L0, h0=rs.H0,
+              d=None, rtol=1e-5, atol=1e-6):
+        alpha, z_f, x_rx = _f64(alpha), _f64(z_f), _f64(x_rx)
+        if alpha.ndim != 1 or z_f.shape != alpha.shape:
+            raise ValueError("Coordinate arrays must have the same length.")
+        l0, h0 = np.float64(l0), np.float64(h0)
+        d = np.float64(l0 + h0) if d is None else np.float64(d)
+        self.params = _capi.Params(float(c1), float(c2), float(l0), float(h0), float(d))
+        self.x_shooter, self.z_shooter = float(x_shooter), float(z_shooter)
+        self.alpha, self.z_f, self.x_rx = alpha, z_f, x_rx
+        _capi.check(self._lib.tofrt_setup(
+            self._ctx, ctypes.byref(self.params), alpha.ctypes.data, z_f.ctypes.data, len(alpha),
+            self.x_shooter, self.z_shooter, x_rx.ctypes.data, len(x_rx), float(rtol), float(atol)))
+        self.K, self.E = len(alpha), len(x_rx)
+        return self
+
+    def lens(self):
+        """lens_1_x, lens_1_z (main_rt.py:338)."""
+        x, z = np.empty(self.K), np.empty(self.K)
+        _capi.check(self._lib.tofrt_lens_host(self._ctx, x.ctypes.data, z.ctypes.data))
+        return x, z
+
+    def kernel_info(self):
+        v = [ctypes.c_int() for _ in range(4)]
+        _capi.check(self._lib.tofrt_kernel_info(self._ctx, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("grid", "block", "smem_bytes", "regs"), (x.value for x in v)))
+
+    def measure_fp64_peak(self):
+        """FP64 thread-instructions/s of this GPU: (DFMA stream, un-fused DMUL+DADD stream)."""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        _capi.check(self._lib.tofrt_measure_fp64_peak(self._ctx, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    # ---- main_rt.py:464-501, host buffers -------------------------------------
+    def tof_table(self, radii, offsets, records=()):
+        radii, offsets = _f64(radii).ravel(), _f64(offsets).ravel()
+        if radii.shape != offsets.shape:
+            raise ValueError("radii and offsets must have the same length")
+        G = len(radii)
+        tof = np.empty((G, self.E))
+        k_hit = np.empty((G, self.E), dtype=np.int32)
+        rec, out = None, {}
+        if records:
+            rec = _capi.RayRecords()
+            for key in records:
+                if key not in RECORD_KEYS:
+                    raise ValueError(f"unknown record {key!r}")
+                shape = (G, 4, self.K) if key == "legs" else (G, self.K)
+                out[key] = np.empty(shape, dtype=np.int32 if key == "idx" else np.float64)
+                setattr(rec, key, out[key].ctypes.data)
+        _capi.check(self._lib.tofrt_table_host(self._ctx, radii.ctypes.data, offsets.ctypes.data, G,
+                                               tof.ctypes.data, k_hit.ctypes.data,
+                                               ctypes.byref(rec) if rec is not None else None))
+        return TofTable(tof, k_hit, out)
+
+    # ---- same, device-resident torch tensors, async on the current stream -------
+    def tof_table_cuda(self, radii, offsets, out_tof=None, out_k_hit=None, records=()):
+        import torch
+        if not (radii.is_cuda and offsets.is_cuda and radii.dtype == torch.float64 and
+                offsets.dtype == torch.float64 and radii.is_contiguous() and offsets.is_contiguous()):
+            raise ValueError("radii/offsets must be contiguous float64 CUDA tensors")
+        if radii.device.index != self.device or radii.shape != offsets.shape:
+            raise ValueError("radii/offsets must live on the engine's device and have the same shape")
+        G = radii.numel()
+        dev = radii.device
+        tof = out_tof if out_tof is not None else torch.empty((G, self.E), dtype=torch.float64, device=dev)
+        k_hit = out_k_hit if out_k_hit is not None else torch.empty((G, self.E), dtype=torch.int32, device=dev)
+        rec, out = None, {}
+        if records:
+            rec = _capi.RayRecords()
+            for key in records:
+                shape = (G, 4, self.K) if key == "legs" else (G, self.K)
+                out[key] = torch.empty(shape, dtype=torch.int32 if key == "idx" else torch.float64, device=dev)
+                setattr(rec, key, out[key].data_ptr())
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _capi.check(self._lib.tofrt_table_dev(self._ctx, radii.data_ptr(), offsets.data_ptr(), G,
+                                              tof.data_ptr(), k_hit.data_ptr(),
+                                              ctypes.byref(rec) if rec is not None else None,
+                                              ctypes.c_void_p(stream)))
+        return TofTable(tof, k_hit, out)
+
+    # ---- main_rt.py:337-441 -----------------------------------------------------
+    def shoot_rays(self, r_outer, pipe_offset, with_idx=False, with_legs=False):
+        recs = ["pipe_x", "pipe_z", "lens2_x", "lens2_z", "target_x"]
+        if with_idx:
+            recs.append("idx")
+        if with_legs:
+            recs.append("legs")
+        t = self.tof_table([r_outer], [pipe_offset], records=recs)
+        lx, lz = self.lens()
+        res = {
+            "lens_1_x": lx, "lens_1_z": lz,
+            "pipe_x": t.records["pipe_x"][0], "pipe_z": t.records["pipe_z"][0],
+            "lens_2_x": t.records["lens2_x"][0], "lens_2_z": t.records["lens2_z"][0],
+            "target_x": t.records["target_x"][0], "target_z": self.z_f.copy(),
+        }
+        if with_idx:
+            res["idx"] = t.records["idx"][0]
+        if with_legs:
+            res["legs"] = t.records["legs"][0]
+        return res

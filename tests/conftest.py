@@ -1,0 +1,41 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return {name: np.load(os.path.join(GOLDEN, name + ".npz"))
+            for name in ("database_2", "compare", "sweep", "rays", "compare_live", "shooters")}
+
+
+@pytest.fixture(scope="session")
+def oracle_libm():
+    from oracle.oracle import Oracle
+    return Oracle(device_math=False)
+
+
+@pytest.fixture(scope="session")
+def oracle_dm():
+    from oracle.oracle import Oracle
+    return Oracle(device_math=True)
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """The product, through the C ABI.  Builds libtofrt.so if the source is newer."""
+    from ray_tracing_ultrasound_b200 import TofEngine, _build
+    if _build.is_stale():
+        _build.build()
+    return TofEngine(0)

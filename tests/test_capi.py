@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library loads and exports every symbol include/tofrt.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tofrt.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tofrt_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    from ray_tracing_ultrasound_b200 import _build, _capi
+    if _build.is_stale():
+        _build.build()
+    lib = ctypes.CDLL(_build.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 9
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tofrt.h but not exported"
+    assert sorted(_capi.EXPORTS) == declared
+    lib.tofrt_version.restype = ctypes.c_int
+    assert lib.tofrt_version() == 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    """The product must fail loudly when there is no CUDA device / extension."""
+    from ray_tracing_ultrasound_b200 import TofEngine, _capi
+    lib = _capi.load()
+    if lib.tofrt_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError):
+        TofEngine(0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ray_tracing_ultrasound_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle's", "").replace("the oracle", "") or f == "tofrt_math.h" \
+                    or "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_reference_setup_matches_golden_inputs(golden):
+    """x_a and alpha are rebuilt with the reference's NumPy expressions, bit for bit."""
+    import numpy as np
+    from ray_tracing_ultrasound_b200 import reference_setup as rs
+    x_a, z_a = rs.transducer()
+    assert np.array_equal(x_a, golden["sweep"]["x_a"])
+    assert np.array_equal(rs.launch_angles(), golden["sweep"]["alpha"])
+    assert np.array_equal(rs.launch_angles(rs.NUM_ALPHA_POINTS_COMPARE), golden["compare_live"]["alpha"])
+    r, o = rs.sweep_grid()
+    assert np.array_equal(r, golden["sweep"]["radius"]) and np.array_equal(o, golden["sweep"]["offset"])
+    assert z_a[0] == 0.21 and rs.launch_angles()[452] == -1.1102230246251565e-16

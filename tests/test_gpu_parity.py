@@ -1,0 +1,232 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the oracle and the
+reference's fixtures.
+
+Bars (BASELINE.json north_star): discrete indices (idx, k_hit) bit-exact;
+travel times within 1e-12 s of the reference.  Against the oracle's device-math
+twin (same elementary functions, gcc-compiled) every output is bit-exact.
+"""
+import numpy as np
+import pytest
+
+from ray_tracing_ultrasound_b200 import reference_setup as rs
+
+pytestmark = pytest.mark.gpu
+
+TOF_TOL = 1e-12  # seconds, north_star
+NOISE_FLOOR = 1e-13
+
+
+def _std(engine, n_alpha=rs.NUM_ALPHA_POINTS_RT, shooter=32, atol=1e-6):
+    x_a, z_a = rs.transducer()
+    alpha, zf = rs.launch_angles(n_alpha), rs.focus_line(n_alpha)
+    engine.setup(alpha, zf, x_a[shooter], z_a[shooter], x_a, atol=atol)
+    return x_a, z_a, alpha, zf
+
+
+def _same(a, b):
+    """bit-exact incl. NaN positions"""
+    return np.array_equal(a, b, equal_nan=True)
+
+
+def test_fixture_sweep_bit_exact_vs_twin_and_within_tol_vs_reference(engine, golden, oracle_dm, oracle_libm):
+    """BASELINE config 1: the main_rt.py default sweep (210 geometries x 65 receivers)."""
+    x_a, z_a, alpha, zf = _std(engine)
+    radii, offsets = rs.sweep_grid()
+    t = engine.tof_table(radii, offsets, records=("idx", "target_x", "pipe_x", "pipe_z", "lens2_x", "lens2_z"))
+    p = oracle_dm.params()
+    # bit-exact twin
+    tof, k_hit, idx = oracle_dm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a, want_idx=True)
+    assert np.array_equal(t.k_hit, k_hit.T)
+    assert np.array_equal(t.records["idx"], idx)
+    assert np.array_equal(t.tof, tof.T)
+    # independent libm oracle: indices equal, times within tolerance
+    tof2, k_hit2, idx2 = oracle_libm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a, want_idx=True)
+    assert np.array_equal(t.k_hit, k_hit2.T)
+    assert np.abs(t.tof - tof2.T).max() <= TOF_TOL
+    # the reference's fixture database_2.csv and the live reference
+    db, sw = golden["database_2"], golden["sweep"]
+    assert np.array_equal(t.hit, db["hitted"].reshape(210, 65))
+    assert np.abs(t.tof - db["tof_total"].reshape(210, 65)).max() <= TOF_TOL
+    assert np.array_equal(t.k_hit, sw["k_hit"])
+    assert np.abs(t.tof - sw["tof"]).max() <= TOF_TOL
+    ridx = sw["idx"].astype(np.int32)
+    gi = np.where(t.records["idx"] < -1, -1, t.records["idx"])
+    differs = (gi != ridx) & (ridx != -2)
+    assert not (differs & (sw["margin"] > NOISE_FLOOR)).any()
+    assert np.array_equal(np.isnan(t.records["target_x"]), np.unpackbits(sw["nan_target"], axis=1)[:, :905].astype(bool))
+    # per-ray records vs the twin, ray by ray
+    for g in (0, 10, 57, 209):
+        res = oracle_dm.shoot_rays(p, radii[g], offsets[g], x_a[32], z_a[32], zf, alpha)
+        for a, b in (("pipe_x", "pipe_x"), ("pipe_z", "pipe_z"), ("lens2_x", "lens_2_x"),
+                     ("lens2_z", "lens_2_z"), ("target_x", "target_x")):
+            assert _same(t.records[a][g], res[b]), (a, g)
+
+
+def test_compare_case_vs_compare_csv(engine, golden, oracle_dm):
+    """main_compare.py: K = N = 1810, r = 0.037, off = 0.0038, legs + hitted(atol 1e-4)."""
+    x_a, z_a, alpha, zf = _std(engine, rs.NUM_ALPHA_POINTS_COMPARE, atol=1e-4)
+    res = engine.shoot_rays(0.037, 0.0038, with_idx=True, with_legs=True)
+    cc, cl = golden["compare"], golden["compare_live"]
+    legs = res["legs"]
+    for ref in (cc["tof"], cl["legs"]):
+        assert np.array_equal(np.isnan(legs), np.isnan(ref))
+        ok = ~np.isnan(legs)
+        assert np.abs(legs[ok] - ref[ok]).max() <= TOF_TOL
+    hitted = np.array([np.isclose(tx, x_a, atol=1e-4).any() for tx in res["target_x"]])
+    assert np.array_equal(hitted, cc["hitted"])
+    p = oracle_dm.params()
+    tw = oracle_dm.shoot_rays(p, 0.037, 0.0038, x_a[32], z_a[32], zf, alpha)
+    assert np.array_equal(res["idx"], tw["idx"])
+    assert _same(res["target_x"], tw["target_x"])
+    assert _same(legs, oracle_dm.ray_legs(p, x_a[32], z_a[32], tw))
+    assert np.array_equal(res["lens_1_x"], tw["lens_1_x"]) and np.array_equal(res["lens_1_z"], tw["lens_1_z"])
+    assert np.array_equal(res["target_z"], zf)
+
+
+def test_random_geometries_bit_exact(engine, oracle_dm, oracle_libm):
+    x_a, z_a, alpha, zf = _std(engine)
+    rng = np.random.default_rng(0)
+    G = 3000
+    radii = rng.uniform(0.005, 0.12, G)
+    offsets = rng.uniform(-0.02, 0.02, G)
+    t = engine.tof_table(radii, offsets, records=("idx", "target_x"))
+    p = oracle_dm.params()
+    tof, k_hit, idx = oracle_dm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a, want_idx=True)
+    assert np.array_equal(t.records["idx"], idx)
+    assert np.array_equal(t.k_hit, k_hit.T)
+    assert np.array_equal(t.tof, tof.T)
+    tof2, k_hit2, _ = oracle_libm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a)
+    assert np.array_equal(t.k_hit, k_hit2.T)
+    assert np.abs(t.tof - tof2.T).max() <= TOF_TOL
+
+
+def test_off_centre_shooters(engine, golden, oracle_dm):
+    sh = golden["shooters"]
+    p = oracle_dm.params()
+    for i, s in enumerate(sh["shooter"]):
+        x_a, z_a, alpha, zf = _std(engine, shooter=int(s))
+        t = engine.tof_table([sh["radius"][i]], [sh["offset"][i]], records=("idx",))
+        assert np.array_equal(t.k_hit[0], sh["k_hit"][i])
+        assert np.abs(t.tof[0] - sh["tof"][i]).max() <= TOF_TOL
+        tof, k_hit, idx = oracle_dm.table(p, [sh["radius"][i]], [sh["offset"][i]], x_a[s], z_a[s], zf, alpha,
+                                          x_a, want_idx=True)
+        assert np.array_equal(t.records["idx"], idx) and np.array_equal(t.tof[0], tof[:, 0])
+
+
+@pytest.mark.parametrize("K", [2, 3, 17, 32, 33, 100, 1810, 4096])
+def test_ray_counts(engine, oracle_dm, K):
+    """K not a multiple of the warp/chunk size, the minimum K = 2, and the largest staged K."""
+    x_a, z_a = rs.transducer()
+    alpha, zf = rs.launch_angles(K), rs.focus_line(K)
+    engine.setup(alpha, zf, x_a[32], z_a[32], x_a)
+    rng = np.random.default_rng(K)
+    G = 40 if K <= 1810 else 12
+    radii, offsets = rng.uniform(0.01, 0.1, G), rng.uniform(-0.01, 0.01, G)
+    t = engine.tof_table(radii, offsets, records=("idx", "target_x"))
+    p = oracle_dm.params()
+    tof, k_hit, idx = oracle_dm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a, want_idx=True)
+    assert np.array_equal(t.records["idx"], idx)
+    assert np.array_equal(t.k_hit, k_hit.T) and np.array_equal(t.tof, tof.T)
+
+
+def test_receiver_edge_cases(engine, oracle_dm):
+    """Unsorted, duplicated, NaN and infinite receivers; one receiver; huge tolerance."""
+    x_a, z_a = rs.transducer()
+    alpha, zf = rs.launch_angles(), rs.focus_line()
+    p = oracle_dm.params()
+    rng = np.random.default_rng(5)
+    radii, offsets = rng.uniform(0.01, 0.1, 64), rng.uniform(-0.01, 0.01, 64)
+    weird = np.concatenate([x_a[::-1][:20], [np.nan, np.inf, -np.inf, 0.0, 0.0, 1e-7, -1e-7, 5.0, -5.0], x_a[10:14]])
+    for x_rx, rtol, atol in ((weird, 1e-5, 1e-6), (np.array([0.0]), 1e-5, 1e-6), (x_a, 1e-5, 1e-3),
+                             (x_a, 0.5, 10.0), (x_a, 0.0, 0.0)):
+        engine.setup(alpha, zf, x_a[32], z_a[32], x_rx, rtol=rtol, atol=atol)
+        t = engine.tof_table(radii, offsets)
+        tof, k_hit, _ = oracle_dm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_rx, rtol=rtol, atol=atol)
+        assert np.array_equal(t.k_hit, k_hit.T), (len(x_rx), rtol, atol)
+        assert np.array_equal(t.tof, tof.T), (len(x_rx), rtol, atol)
+
+
+def test_degenerate_geometries(engine, oracle_dm):
+    """Rays that miss the pipe (the reference crashes there: NaN-out is the documented
+    extension), pipe swallowing the lens, zero / negative / NaN radius, huge offsets."""
+    x_a, z_a, alpha, zf = _std(engine)
+    radii = np.array([1e-4, 0.001, 0.01, 0.2, 0.5, 0.0, -0.01, np.nan, 0.05, 0.05, 0.05, 1e-9, 0.0884, 0.03])
+    offsets = np.array([0.0, 0.05, 0.03, 0.0, 0.1, 0.0, 0.0, 0.0, np.nan, 1.0, -0.06, 0.0, 0.0, np.inf])
+    t = engine.tof_table(radii, offsets, records=("idx", "target_x", "pipe_x", "lens2_x"))
+    p = oracle_dm.params()
+    tof, k_hit, idx = oracle_dm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a, want_idx=True)
+    assert np.array_equal(t.records["idx"], idx)
+    assert np.array_equal(t.k_hit, k_hit.T) and np.array_equal(t.tof, tof.T)
+    for g in range(len(radii)):
+        res = oracle_dm.shoot_rays(p, radii[g], offsets[g], x_a[32], z_a[32], zf, alpha)
+        assert _same(t.records["target_x"][g], res["target_x"]), g
+        assert _same(t.records["pipe_x"][g], res["pipe_x"]), g
+        assert _same(t.records["lens2_x"][g], res["lens_2_x"]), g
+
+
+def test_argument_errors_and_empty_input(engine):
+    x_a, z_a = rs.transducer()
+    with pytest.raises(ValueError):  # main_rt.py:24-29
+        engine.setup(np.array([0.0]), np.array([0.21]), 0.0, 0.21, x_a)
+    with pytest.raises(ValueError):
+        engine.setup(np.zeros(4), np.zeros(5), 0.0, 0.21, x_a)
+    _std(engine)
+    t = engine.tof_table([], [])
+    assert t.tof.shape == (0, 65) and t.k_hit.shape == (0, 65)
+    with pytest.raises(ValueError):
+        engine.tof_table([0.01, 0.02], [0.0])
+
+
+def test_device_resident_api_matches_host_api(engine):
+    import torch
+    x_a, z_a, alpha, zf = _std(engine)
+    radii, offsets = rs.synthetic_grid(48, 40)
+    th = engine.tof_table(radii, offsets)
+    r_d = torch.from_numpy(radii).cuda()
+    o_d = torch.from_numpy(offsets).cuda()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        td = engine.tof_table_cuda(r_d, o_d, records=("idx",))
+    s.synchronize()
+    assert np.array_equal(td.tof.cpu().numpy(), th.tof)
+    assert np.array_equal(td.k_hit.cpu().numpy(), th.k_hit)
+    # determinism: same bytes on a second run
+    td2 = engine.tof_table_cuda(r_d, o_d)
+    torch.cuda.synchronize()
+    assert torch.equal(td.tof, td2.tof) and torch.equal(td.k_hit, td2.k_hit)
+
+
+def test_full_size_grid_properties(engine, oracle_dm):
+    """BASELINE config 3 at full size (129 receivers, 1024 x 1024 geometries): the table is
+    checked through size-independent properties -- a random subsample against the oracle,
+    sub-grid consistency (a slice recomputed alone gives the same bytes), and invariants."""
+    import torch
+    x_a, z_a = rs.transducer(num_elements=128)
+    alpha, zf = rs.launch_angles(), rs.focus_line()
+    engine.setup(alpha, zf, x_a[64], z_a[64], x_a)
+    radii, offsets = rs.synthetic_grid(1024, 1024)
+    r_d, o_d = torch.from_numpy(radii).cuda(), torch.from_numpy(offsets).cuda()
+    t = engine.tof_table_cuda(r_d, o_d)
+    torch.cuda.synchronize()
+    G, E = len(radii), len(x_a)
+    assert t.tof.shape == (G, E)
+    k_hit, tof = t.k_hit, t.tof
+    # invariants: tof == 0 exactly where not hit, plausible where hit, k_hit in range
+    assert bool(((k_hit >= -1) & (k_hit < len(alpha))).all())
+    assert bool(((tof == 0) == (k_hit < 0)).all())
+    hit_t = tof[k_hit >= 0]
+    assert float(hit_t.min()) > 3e-5 and float(hit_t.max()) < 3e-4
+    assert bool((k_hit[:, 64] >= 0).any())
+    # random subsample vs the bit-exact twin
+    rng = np.random.default_rng(0)
+    sel = np.sort(rng.choice(G, 512, replace=False))
+    p = oracle_dm.params()
+    tof_o, k_o, _ = oracle_dm.table(p, radii[sel], offsets[sel], x_a[64], z_a[64], zf, alpha, x_a)
+    sel_d = torch.from_numpy(sel).cuda()
+    assert np.array_equal(k_hit[sel_d].cpu().numpy(), k_o.T)
+    assert np.array_equal(tof[sel_d].cpu().numpy(), tof_o.T)
+    # a contiguous slice recomputed on its own gives identical bytes (what sharding relies on)
+    lo, hi = 300_000, 300_000 + 4096
+    t2 = engine.tof_table_cuda(r_d[lo:hi].contiguous(), o_d[lo:hi].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(t2.tof, tof[lo:hi]) and torch.equal(t2.k_hit, k_hit[lo:hi])
