@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
             // fast path precondition: every diff is finite, so only {-,0,+} occur
             const bool fast = valid && S.tables_ok && fabs(m) < 1e150 && fabs(b) < 1e150;
             int flagged = -1;
+            unsigned gmin = 0xffffffffu;  // min over all chunks of the high words (see below)
             {
                 unsigned hp = hi32(line_diff(s_lens[0], m, b));
                 for (int base = 1; base < Npad; base += kChunk) {
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
                         mx = __vimax3_u32(mx, ha, hb);
                         hp = hb;
                     }
+                    gmin = min(gmin, mn);
                     // sign differs inside the chunk, or a +-0 (high word 0 / 0x80000000) occurred
                     bool flag = ((int)(mn ^ mx) < 0) || ((mn << 1) == 0u);
                     if (flag && flagged < 0) flagged = base;
@@ -284,28 +286,38 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
                 }
             }
             int idx = -1;  // >= 0 segment, -1 none
-            if (valid) {
-                if (!fast) {
-                    idx = scan_exact_from(s_lens, N, m, b, 0);
-                } else if (flagged >= 0) {
-                    // resolve the exact index inside the flagged chunk (samples flagged-1 .. flagged+kChunk-1)
-                    int j0 = flagged - 1;
-                    int jend = min(flagged + kChunk - 1, N - 1);
-                    int cprev = sign_class(line_diff(s_lens[j0], m, b));
-                    for (int j = j0; j < jend; ++j) {
-                        int cnext = sign_class(line_diff(s_lens[j + 1], m, b));
-                        if (class_change(cprev, cnext)) { idx = j; break; }
-                        cprev = cnext;
-                    }
-                    // conservative flag without a real change (a denormal diff): keep going exactly
-                    if (idx < 0 && jend < N - 1) idx = scan_exact_from(s_lens, N, m, b, jend);
+            if (fast && flagged >= 0) {
+                // resolve the exact index inside the flagged chunk without a data-dependent loop:
+                // classes (-1, 0, +1) of samples flagged-1 .. flagged+kChunk-1 (all finite here),
+                // bit u of `chg` = class changes between samples j0+u and j0+u+1
+                const int j0 = flagged - 1;
+                double d = line_diff(s_lens[j0], m, b);
+                int cprev = (((unsigned)__double2hiint(d) << 1) | (unsigned)__double2loint(d)) ? (__double2hiint(d) >> 31) | 1 : 0;
+                unsigned chg = 0;
+#pragma unroll
+                for (int u = 0; u < kChunk; ++u) {
+                    d = line_diff(s_lens[j0 + u + 1], m, b);
+                    int cnext = (((unsigned)__double2hiint(d) << 1) | (unsigned)__double2loint(d)) ? (__double2hiint(d) >> 31) | 1 : 0;
+                    chg |= (cnext != cprev ? 1u : 0u) << u;
+                    cprev = cnext;
                 }
+                if (chg) idx = j0 + __ffs(chg) - 1;  // padding repeats the last sample: never a change there
+            }
+            if (valid && idx < 0) {
+                if (!fast) idx = scan_exact_from(s_lens, N, m, b, 0);
+                // conservative flag without a real change (a denormal diff): keep going exactly
+                else if (flagged >= 0 && flagged + kChunk - 1 < N - 1)
+                    idx = scan_exact_from(s_lens, N, m, b, flagged + kChunk - 1);
             }
             // ---- main_rt.py:84-96 no crossing: is a sample on the line (|diff| <= 1e-8)? ----
-            // warp-cooperative: the 32 lanes test 32 consecutive samples of one ray at a time
+            // All diffs of such a ray have one sign, so the unsigned minimum of their high words is
+            // the high word of min|diff|: only rays that come within 1e-8 of a sample (hi <= hi(1e-8))
+            // need the test.  It is warp-cooperative: 32 lanes take 32 consecutive samples of one ray.
             int on_sample = -1;
             {
-                unsigned need = __ballot_sync(FULL, valid && idx < 0);
+                bool maybe = valid && idx < 0 &&
+                             (!fast || flagged >= 0 || (gmin & 0x7fffffffu) <= 0x3e45798eu /* hi32(1e-8) */);
+                unsigned need = __ballot_sync(FULL, maybe);
                 while (need) {
                     int src = __ffs(need) - 1;
                     need &= need - 1;
