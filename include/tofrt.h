@@ -79,6 +79,31 @@ int tofrt_setup(tofrt_ctx *ctx, const tofrt_params *params, const double *alpha,
                 int K, double x_shooter, double z_shooter, const double *x_rx, int E, double rtol,
                 double atol);
 
+/* Options.  TOFRT_OPT_SEARCH selects how the return-path entry index of
+ * find_line_curve_intersection (main_rt.py:78-99) is found:
+ *   TOFRT_SEARCH_SCAN    the reference's literal first-sign-change scan over all
+ *                        N lens samples (early exit per warp);
+ *   TOFRT_SEARCH_GUIDED  (default) bracketed search that returns the identical
+ *                        index in O(log N) evaluations whenever the sampled lens
+ *                        is a strictly concave/convex polyline, and falls back to
+ *                        the scan for any ray whose signs are within rounding
+ *                        error of zero.  Results are bit-identical by construction. */
+#define TOFRT_OPT_SEARCH 1
+#define TOFRT_SEARCH_SCAN 0
+#define TOFRT_SEARCH_GUIDED 1
+int tofrt_set_option(tofrt_ctx *ctx, int option, int value);
+
+/* Facts about the current setup: TOFRT_INFO_SHAPE -> +1 concave / -1 convex /
+ * 0 neither (guided search disabled); TOFRT_INFO_SEARCH -> current search mode. */
+#define TOFRT_INFO_SHAPE 1
+#define TOFRT_INFO_SEARCH 2
+int tofrt_get_info(tofrt_ctx *ctx, int what);
+
+/* Search statistics of the most recent table call on this context (synchronises):
+ * [0] rays traced, [1] rays whose index needed the O(N) scan, [2] 32-ray groups that
+ * ran the scan loop, [3] rays that needed the |diff| <= 1e-8 on-sample pass. */
+int tofrt_last_stats(tofrt_ctx *ctx, unsigned long long *stats4);
+
 /* Lens samples of the current setup, "lens_1_x"/"lens_1_z" (main_rt.py:338). */
 int tofrt_lens_host(tofrt_ctx *ctx, double *lens_x, double *lens_z);
 

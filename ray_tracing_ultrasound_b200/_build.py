@@ -4,7 +4,7 @@ import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtofrt.so")
+LIB_PATH = os.environ.get("TOFRT_LIB") or os.path.join(HERE, "libtofrt.so")  # TOFRT_LIB: tuning variants
 SOURCES = [os.path.join(HERE, "csrc", "tofrt_kernels.cu")]
 HEADERS = [os.path.join(HERE, "csrc", "tofrt_math.h"),
            os.path.join(os.path.dirname(HERE), "include", "tofrt.h")]
@@ -32,14 +32,16 @@ def is_stale():
     return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
     """Compile csrc/*.cu -> libtofrt.so.  Cross-compiles without a GPU."""
-    if not force and not is_stale():
+    out = out or LIB_PATH
+    if not force and out == LIB_PATH and not is_stale():
         return LIB_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    cmd = ([nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+           + ["-o", out] + SOURCES)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out

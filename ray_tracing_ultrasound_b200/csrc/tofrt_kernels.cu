@@ -42,7 +42,13 @@
 
 namespace {
 
-constexpr int kThreads = 512;         // 16 warps per CTA, one CTA per SM
+#ifndef TOFRT_THREADS
+#define TOFRT_THREADS 1024
+#endif
+#ifndef TOFRT_MIN_BLOCKS
+#define TOFRT_MIN_BLOCKS 1
+#endif
+constexpr int kThreads = TOFRT_THREADS;  // warps per CTA = kThreads / 32
 constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 16;            // lens samples per early-exit check
 constexpr int kNoHit = 0x7fffffff;
@@ -57,8 +63,13 @@ struct DevSetup {
     double rtol, atol, tol_max;              // np.isclose tolerances, and an upper bound of atol+rtol|x_e|
     double rx_min, rx_max;                   // finite receiver range
     int K, Npad, E, E_sorted, has_nonfinite_rx, tables_ok;
+    int shape;      // +1: sampled lens strictly concave in x, -1: strictly convex, 0: neither (no guided search)
+    int guided;     // search mode: 1 = guided (bracketed) search, 0 = the reference's literal O(N) scan
+    int log2n;      // ceil(log2(K)) + 1 bisection steps
+    double X, Z;    // max |x_p|, max |z_p|  (rounding-error bound of a diff)
     // tables in global memory
     const double2 *lens;   // [Npad] (x_p, z_p), padded with copies of the last sample
+    const double2 *seg;    // [K-1] chord (m_seg, b_seg) of main_rt.py:127-128
     const double *a_pq, *b_pq, *phi_pq, *z_f, *leg1;  // [K]
     const double *x_rx;    // [E] as given
     const double *xs;      // [E_sorted] finite receivers, ascending
@@ -72,6 +83,7 @@ struct TableArgs {
     int *k_hit;
     tofrt_ray_records rec;
     unsigned long long *counter;
+    unsigned long long *stats;  // [4]: rays traced, rays that needed the O(N) scan, warp-chunks that ran it, on-sample passes
 };
 
 // ---- small device helpers ---------------------------------------------------
@@ -149,6 +161,17 @@ __global__ void tofrt_prepare_kernel(DevSetup S, const double *alpha, double2 *l
     leg1[k] = dist2d(S.x_sh, S.z_sh, x_p, z_p) / S.c1;
 }
 
+// chords of the sampled lens, main_rt.py:127-128 (geometry-independent, so computed once)
+__global__ void tofrt_chord_kernel(int K, const double2 *lens, double2 *seg)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= K - 1) return;
+    double2 p1 = lens[j], p2 = lens[j + 1];
+    double m_seg = (p2.y - p1.y) / (p2.x - p1.x);
+    double b_seg = p1.y - m_seg * p1.x;
+    seg[j] = make_double2(m_seg, b_seg);
+}
+
 // ---- exact (slow) pieces of find_line_curve_intersection ------------------------
 
 // first j in [j0, N-2] with a sign-class change between samples j and j+1, else -1
@@ -164,18 +187,17 @@ __device__ __noinline__ int scan_exact_from(const double2 *lens, int N, double m
 }
 
 // main_rt.py:106-168: intersect the line with chord (idx, idx+1)
-__device__ __forceinline__ void chord_intersection(const double2 *lens, int idx, double m, double b, double *xi,
-                                                   double *zi)
+__device__ __forceinline__ void chord_intersection(const double2 *lens, const double2 *seg, int idx, double m,
+                                                   double b, double *xi, double *zi)
 {
-    double2 p1 = lens[idx], p2 = lens[idx + 1];
+    double2 p1 = lens[idx], p2 = lens[idx + 1], sg = seg[idx];
     double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
     double rx = NAN, ry = NAN;
     if (np_isclose(x1, x2, 1e-5, 1e-8)) {  // :110-123 vertical chord
         double y_int = m * x1 + b;
         if (y_int >= py_min(y1, y2) - 1e-9 && y_int <= py_max(y1, y2) + 1e-9) { rx = x1; ry = y_int; }
     } else {
-        double m_seg = (y2 - y1) / (x2 - x1);
-        double b_seg = y1 - m_seg * x1;
+        double m_seg = sg.x, b_seg = sg.y;  // :127-128
         if (np_isclose(m, m_seg, 1e-5, 1e-8)) {  // :131-144 parallel
             if (np_isclose(b, b_seg, 1e-5, 1e-8)) { rx = (x1 + x2) / 2.0; ry = m * rx + b; }
         } else {  // :147-168
@@ -191,25 +213,20 @@ __device__ __forceinline__ void chord_intersection(const double2 *lens, int idx,
 }
 
 // ---- the table kernel -----------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, TableArgs T)
+__global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel(DevSetup S, TableArgs T)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = S.K, N = S.K, Npad = S.Npad, E = S.E;
     // shared-memory carve-up
     double2 *s_lens = reinterpret_cast<double2 *>(smem_raw);
-    double *s_a = reinterpret_cast<double *>(s_lens + Npad);
-    double *s_b = s_a + K;
-    double *s_phi = s_b + K;
-    double *s_zf = s_phi + K;
-    double *s_xs = s_zf + K;
+    double2 *s_seg = s_lens + Npad;                  // [K-1] (+1 pad)
+    double *s_xs = reinterpret_cast<double *>(s_seg + K);
     double *s_tof = s_xs + S.E_sorted;               // [kWarps][E]
     int *s_perm = reinterpret_cast<int *>(s_tof + (size_t)kWarps * E);
     int *s_khit = s_perm + S.E_sorted;               // [kWarps][E]
 
     for (int i = threadIdx.x; i < Npad; i += kThreads) s_lens[i] = S.lens[i];
-    for (int i = threadIdx.x; i < K; i += kThreads) {
-        s_a[i] = S.a_pq[i]; s_b[i] = S.b_pq[i]; s_phi[i] = S.phi_pq[i]; s_zf[i] = S.z_f[i];
-    }
+    for (int i = threadIdx.x; i < K - 1; i += kThreads) s_seg[i] = S.seg[i];
     for (int i = threadIdx.x; i < S.E_sorted; i += kThreads) { s_xs[i] = S.xs[i]; s_perm[i] = S.perm[i]; }
     __syncthreads();
 
@@ -218,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
     int *w_khit = s_khit + (size_t)warp * E;
     const int nchunks = (K + 31) >> 5;
     const unsigned FULL = 0xffffffffu;
+    unsigned st_rays = 0, st_scan_rays = 0, st_scan_warps = 0, st_onsample = 0;
 
     for (;;) {
         unsigned long long g64 = 0;
@@ -234,7 +252,9 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
             const int k = (c << 5) + lane;
             const bool valid = k < K;
             const int kk = valid ? k : K - 1;
-            const double a_pq = s_a[kk], b_pq = s_b[kk], phi_pq = s_phi[kk];
+            // per-ray constants of the shot: one coalesced, L1-resident load per 32 rays
+            const double a_pq = __ldg(S.a_pq + kk), b_pq = __ldg(S.b_pq + kk), phi_pq = __ldg(S.phi_pq + kk);
+            const double z_f = __ldg(S.z_f + kk);
 
             // ---- main_rt.py:351-364 pipe intersection, upper root ----
             double x_q, z_q;
@@ -264,9 +284,81 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
             // ---- main_rt.py:78-99 first sign change over the sampled lens ----
             // fast path precondition: every diff is finite, so only {-,0,+} occur
             const bool fast = valid && S.tables_ok && fabs(m) < 1e150 && fabs(b) < 1e150;
+            int idx = -1;             // >= 0 segment, -1 none
+            bool need_scan = fast;    // lanes whose index the O(N) scan below still has to find
+            bool skip_on_sample = false;
+            if (S.guided && S.shape != 0) {
+                // ---- guided search: same idx as the scan, in O(log N) diffs ------------------
+                // g_j = shape * diff_j is, in exact arithmetic, a concave sequence over the sampled
+                // lens (chord slopes strictly monotone, checked by tofrt_setup), and a computed diff
+                // differs from the exact one by < tol = 2^-48 (|m| X + |b| + Z).  So a diff beyond
+                // +-tol has a certain sign, a concave sequence is >= the smaller of two of its values
+                // in between, and it is monotone on either side of its maximum: that brackets the
+                // first sign change to [lo, lo+1] with every earlier sign known; the exact scan then
+                // starts at lo.  Anything uncertain (|diff| <= tol where it matters) falls back to the
+                // full scan, so the result is identical by construction.
+                const double sh = (double)S.shape;
+                const double tol = (fabs(m) * S.X + fabs(b) + S.Z) * 0x1p-48 + 1e-290;
+                const double g0 = sh * line_diff(s_lens[0], m, b);
+                const double gN = sh * line_diff(s_lens[N - 1], m, b);
+                // maximum of g: first chord whose slope (times shape) is <= shape*m
+                int jm;
+                {
+                    const double ms = sh * m;
+                    int l = 0, r = N - 1;  // answer in [0, N-1]
+                    for (int it = 0; it < S.log2n; ++it) {
+                        int mid = (l + r) >> 1;
+                        bool go = (l < r) && (sh * s_seg[min(mid, N - 2)].x > ms);
+                        l = go ? mid + 1 : l;
+                        r = (l < r && !go) ? mid : r;
+                    }
+                    jm = l;
+                }
+                int lo = 0, hi = 0;
+                bool bracket = false, certain_none = false;
+                double edge = 0.0;  // |diff| closest to zero when there is certainly no change
+                if (fast) {
+                    if (g0 > tol) {
+                        if (gN > tol) { certain_none = true; edge = fmin(g0, gN) - tol; }
+                        else { bracket = true; lo = 0; hi = N - 1; }
+                    } else if (g0 < -tol) {
+                        const double gm = sh * line_diff(s_lens[jm], m, b);
+                        if (gm < -tol) { certain_none = true; edge = -gm - tol; }
+                        else if (gm > tol) { bracket = true; lo = 0; hi = jm; }
+                    }
+                }
+                // bisection: invariant g_lo beyond tol with the sign of g_0 (so is every sample before lo)
+                const bool pos0 = g0 > 0;
+                for (int it = 0; it < S.log2n; ++it) {
+                    int mid = (lo + hi) >> 1;
+                    double gmid = sh * line_diff(s_lens[mid], m, b);
+                    bool same = pos0 ? (gmid > tol) : (gmid < -tol);
+                    bool act = bracket && (hi - lo > 1);
+                    lo = (act && same) ? mid : lo;
+                    hi = (act && !same) ? mid : hi;
+                }
+                if (bracket) {
+                    // exact classes from lo on (normally one step)
+                    int cprev = sign_class(line_diff(s_lens[lo], m, b));
+                    int j = lo;
+                    for (; j + 1 < N; ++j) {
+                        int cnext = sign_class(line_diff(s_lens[j + 1], m, b));
+                        if (class_change(cprev, cnext)) break;
+                        cprev = cnext;
+                    }
+                    if (j + 1 < N) { idx = j; need_scan = false; }
+                    else { need_scan = false; }  // no change after lo either: certainly none before it
+                    // (possible only when the far end is within tol of zero; the on-sample test below decides)
+                } else if (certain_none) {
+                    need_scan = false;
+                    skip_on_sample = edge > 1e-8;  // every |diff| > 1e-8: main_rt.py:86-96 returns None
+                }
+            }
             int flagged = -1;
             unsigned gmin = 0xffffffffu;  // min over all chunks of the high words (see below)
-            {
+            st_rays += valid; st_scan_rays += need_scan;
+            if (__any_sync(FULL, need_scan)) {
+                st_scan_warps += (lane == 0);
                 unsigned hp = hi32(line_diff(s_lens[0], m, b));
                 for (int base = 1; base < Npad; base += kChunk) {
                     unsigned mn = hp, mx = hp;
@@ -282,11 +374,10 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
                     // sign differs inside the chunk, or a +-0 (high word 0 / 0x80000000) occurred
                     bool flag = ((int)(mn ^ mx) < 0) || ((mn << 1) == 0u);
                     if (flag && flagged < 0) flagged = base;
-                    if (__all_sync(FULL, flagged >= 0 || !fast)) break;
+                    if (__all_sync(FULL, flagged >= 0 || !need_scan)) break;
                 }
             }
-            int idx = -1;  // >= 0 segment, -1 none
-            if (fast && flagged >= 0) {
+            if (need_scan && flagged >= 0) {
                 // resolve the exact index inside the flagged chunk without a data-dependent loop:
                 // classes (-1, 0, +1) of samples flagged-1 .. flagged+kChunk-1 (all finite here),
                 // bit u of `chg` = class changes between samples j0+u and j0+u+1
@@ -306,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
             if (valid && idx < 0) {
                 if (!fast) idx = scan_exact_from(s_lens, N, m, b, 0);
                 // conservative flag without a real change (a denormal diff): keep going exactly
-                else if (flagged >= 0 && flagged + kChunk - 1 < N - 1)
+                else if (need_scan && flagged >= 0 && flagged + kChunk - 1 < N - 1)
                     idx = scan_exact_from(s_lens, N, m, b, flagged + kChunk - 1);
             }
             // ---- main_rt.py:84-96 no crossing: is a sample on the line (|diff| <= 1e-8)? ----
@@ -315,9 +406,11 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
             // need the test.  It is warp-cooperative: 32 lanes take 32 consecutive samples of one ray.
             int on_sample = -1;
             {
-                bool maybe = valid && idx < 0 &&
-                             (!fast || flagged >= 0 || (gmin & 0x7fffffffu) <= 0x3e45798eu /* hi32(1e-8) */);
+                bool maybe = valid && idx < 0 && !skip_on_sample &&
+                             (!fast || !need_scan || flagged >= 0 ||
+                              (gmin & 0x7fffffffu) <= 0x3e45798eu /* hi32(1e-8) */);
                 unsigned need = __ballot_sync(FULL, maybe);
+                st_onsample += (lane == 0) ? __popc(need) : 0;
                 while (need) {
                     int src = __ffs(need) - 1;
                     need &= need - 1;
@@ -332,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
                 }
             }
             double ix = NAN, iz = NAN;
-            if (idx >= 0) chord_intersection(s_lens, idx, m, b, &ix, &iz);
+            if (idx >= 0) chord_intersection(s_lens, s_seg, idx, m, b, &ix, &iz);
             else if (on_sample >= 0) { double2 s = s_lens[on_sample]; ix = s.x; iz = s.y; }
 
             // ---- main_rt.py:396-405 refraction back into the lens, landing point ----
@@ -345,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
                 double phi_last = refract(phi_l, dz, dx, S.c1_over_c2);
                 double a_i = tofrt_tan(phi_last);
                 double b_i = iz - a_i * ix;
-                target_x = (s_zf[kk] - b_i) / a_i;
+                target_x = (z_f - b_i) / a_i;
             }
 
             // ---- optional per-ray records ----
@@ -390,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
                     double t1 = S.leg1[kk];
                     double t2 = dist2d(p.x, p.y, x_q, z_q) / S.c2;
                     double t3 = dist2d(x_q, z_q, ix, iz) / S.c2;
-                    double t4 = dist2d(ix, iz, target_x, s_zf[kk]) / S.c1;
+                    double t4 = dist2d(ix, iz, target_x, z_f) / S.c1;
                     if (want_legs) {
                         size_t o = (size_t)g * 4 * K + k;
                         T.rec.legs[o] = t1; T.rec.legs[o + K] = t2;
@@ -421,6 +514,13 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel(DevSetup S, Ta
             T.k_hit[(size_t)g * E + e] = kh == kNoHit ? -1 : kh;
         }
         __syncwarp();
+    }
+    if (T.stats) {
+        st_rays = __reduce_add_sync(FULL, st_rays); st_scan_rays = __reduce_add_sync(FULL, st_scan_rays);
+        if (lane == 0) {
+            atomicAdd(T.stats + 0, (unsigned long long)st_rays); atomicAdd(T.stats + 1, (unsigned long long)st_scan_rays);
+            atomicAdd(T.stats + 2, (unsigned long long)st_scan_warps); atomicAdd(T.stats + 3, (unsigned long long)st_onsample);
+        }
     }
 }
 
@@ -472,18 +572,20 @@ struct tofrt_ctx {
     DevSetup S{};
     int K = 0, E = 0;
     size_t smem = 0;
+    int ctas_per_sm = 1;
     // device buffers owned by the context
     double *d_alpha = nullptr, *d_zf = nullptr, *d_a = nullptr, *d_b = nullptr, *d_phi = nullptr, *d_leg1 = nullptr;
-    double2 *d_lens = nullptr;
+    double2 *d_lens = nullptr, *d_seg = nullptr;
+    int opt_guided = 1;
     double *d_xrx = nullptr, *d_xs = nullptr;
     int *d_perm = nullptr, *d_bad = nullptr;
     unsigned long long *d_counter = nullptr;
     void free_all()
     {
         cudaFree(d_alpha); cudaFree(d_zf); cudaFree(d_a); cudaFree(d_b); cudaFree(d_phi); cudaFree(d_leg1);
-        cudaFree(d_lens); cudaFree(d_xrx); cudaFree(d_xs); cudaFree(d_perm); cudaFree(d_bad);
+        cudaFree(d_lens); cudaFree(d_seg); cudaFree(d_xrx); cudaFree(d_xs); cudaFree(d_perm); cudaFree(d_bad);
         d_alpha = d_zf = d_a = d_b = d_phi = d_leg1 = d_xrx = d_xs = nullptr;
-        d_lens = nullptr; d_perm = d_bad = nullptr;
+        d_lens = d_seg = nullptr; d_perm = d_bad = nullptr;
     }
 };
 
@@ -507,7 +609,7 @@ int tofrt_create(tofrt_ctx **out, int device)
     tofrt_ctx *c = new tofrt_ctx();
     c->device = device;
     cudaError_t e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, 5 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_bad, sizeof(int));
     if (e != cudaSuccess) {
         delete c;
@@ -576,7 +678,7 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
     S.rx_min = xs.empty() ? 1.0 : xs.front();
     S.rx_max = xs.empty() ? -1.0 : xs.back();
 
-    const size_t smem = (size_t)S.Npad * sizeof(double2) + (size_t)K * 4 * sizeof(double) +
+    const size_t smem = (size_t)(S.Npad + K) * sizeof(double2) +
                         (size_t)S.E_sorted * (sizeof(double) + sizeof(int)) +
                         (size_t)kWarps * E * (sizeof(double) + sizeof(int)) + 16;
     if (smem > 227 * 1024)
@@ -589,6 +691,7 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
     CUDA_TRY(cudaMalloc(&c->d_phi, sizeof(double) * K));
     CUDA_TRY(cudaMalloc(&c->d_leg1, sizeof(double) * K));
     CUDA_TRY(cudaMalloc(&c->d_lens, sizeof(double2) * S.Npad));
+    CUDA_TRY(cudaMalloc(&c->d_seg, sizeof(double2) * K));
     CUDA_TRY(cudaMalloc(&c->d_xrx, sizeof(double) * E));
     CUDA_TRY(cudaMalloc(&c->d_xs, sizeof(double) * std::max(1, S.E_sorted)));
     CUDA_TRY(cudaMalloc(&c->d_perm, sizeof(int) * std::max(1, S.E_sorted)));
@@ -600,20 +703,83 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
         CUDA_TRY(cudaMemcpy(c->d_perm, order.data(), sizeof(int) * S.E_sorted, cudaMemcpyHostToDevice));
     }
     CUDA_TRY(cudaMemset(c->d_bad, 0, sizeof(int)));
-    S.lens = c->d_lens; S.a_pq = c->d_a; S.b_pq = c->d_b; S.phi_pq = c->d_phi; S.z_f = c->d_zf;
+    S.lens = c->d_lens; S.seg = c->d_seg; S.a_pq = c->d_a; S.b_pq = c->d_b; S.phi_pq = c->d_phi; S.z_f = c->d_zf;
     S.leg1 = c->d_leg1; S.x_rx = c->d_xrx; S.xs = c->d_xs; S.perm = c->d_perm;
 
     tofrt_prepare_kernel<<<(S.Npad + 127) / 128, 128>>>(S, c->d_alpha, c->d_lens, c->d_a, c->d_b, c->d_phi,
                                                         c->d_leg1, c->d_bad);
     CUDA_TRY(cudaGetLastError());
+    tofrt_chord_kernel<<<(K + 127) / 128, 128>>>(K, c->d_lens, c->d_seg);
+    CUDA_TRY(cudaGetLastError());
     int bad = 0;
     CUDA_TRY(cudaMemcpy(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
     S.tables_ok = bad ? 0 : 1;
+    // Facts the guided search relies on, verified here on the actual table: abscissae strictly
+    // increasing and chord slopes strictly monotone by more than their own rounding error
+    // (=> the sampled lens is a strictly concave / convex polyline in exact arithmetic).
+    {
+        std::vector<double2> hl(K), hs(K);
+        CUDA_TRY(cudaMemcpy(hl.data(), c->d_lens, sizeof(double2) * K, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(hs.data(), c->d_seg, sizeof(double2) * (K - 1), cudaMemcpyDeviceToHost));
+        bool incr = true, dec = true, inc = true;
+        double X = 0, Z = 0;
+        for (int j = 0; j < K; ++j) {
+            X = std::max(X, std::fabs(hl[j].x));
+            Z = std::max(Z, std::fabs(hl[j].y));
+            if (j + 1 < K && !(hl[j + 1].x > hl[j].x)) incr = false;
+        }
+        for (int j = 0; j + 2 < K; ++j) {
+            double a = hs[j].x, b2 = hs[j + 1].x;
+            double guard = 16 * 2.220446049250313e-16 * std::max(std::fabs(a), std::fabs(b2));
+            if (!(a - b2 > guard)) dec = false;
+            if (!(b2 - a > guard)) inc = false;
+        }
+        S.X = X; S.Z = Z;
+        S.shape = (S.tables_ok && incr && K >= 3) ? (dec ? 1 : (inc ? -1 : 0)) : 0;
+        int lg = 1;
+        while ((1 << lg) < K) ++lg;
+        S.log2n = lg + 1;
+    }
+    S.guided = c->opt_guided;
 
     CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel, kThreads, smem));
+    c->ctas_per_sm = std::max(1, occ);
     c->S = S; c->K = K; c->E = E; c->smem = smem;
     c->ready = true;
     return TOFRT_OK;
+}
+
+int tofrt_set_option(tofrt_ctx *c, int option, int value)
+{
+    if (!c) return fail(TOFRT_E_BADARG, "tofrt_set_option: ctx is NULL");
+    if (option == TOFRT_OPT_SEARCH) {
+        if (value != TOFRT_SEARCH_SCAN && value != TOFRT_SEARCH_GUIDED)
+            return fail(TOFRT_E_BADARG, "tofrt_set_option: bad search mode");
+        c->opt_guided = value;
+        c->S.guided = value;
+        return TOFRT_OK;
+    }
+    return fail(TOFRT_E_BADARG, "tofrt_set_option: unknown option");
+}
+
+int tofrt_last_stats(tofrt_ctx *c, unsigned long long *stats4)
+{
+    if (!c || !stats4) return fail(TOFRT_E_BADARG, "tofrt_last_stats: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpy(stats4, c->d_counter + 1, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return TOFRT_OK;
+}
+
+int tofrt_get_info(tofrt_ctx *c, int what)
+{
+    if (!c) return TOFRT_E_BADARG;
+    switch (what) {
+    case TOFRT_INFO_SHAPE: return c->ready ? c->S.shape : 0;
+    case TOFRT_INFO_SEARCH: return c->opt_guided;
+    default: return TOFRT_E_BADARG;
+    }
 }
 
 int tofrt_lens_host(tofrt_ctx *c, double *lens_x, double *lens_z)
@@ -640,9 +806,10 @@ int tofrt_table_dev(tofrt_ctx *c, const double *d_radius, const double *d_offset
     T.radius = d_radius; T.offset = d_offset; T.G = G; T.tof = d_tof; T.k_hit = d_k_hit;
     if (d_rec) T.rec = *d_rec;
     T.counter = c->d_counter;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), st));
+    T.stats = c->d_counter + 1;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
     long long warps_needed = G;
-    int grid = (int)std::min<long long>(c->sm_count, (warps_needed + kWarps - 1) / kWarps);
+    int grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, (warps_needed + kWarps - 1) / kWarps);
     tofrt_table_kernel<<<grid, kThreads, c->smem, st>>>(c->S, T);
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
@@ -741,7 +908,7 @@ int tofrt_kernel_info(tofrt_ctx *c, int *grid, int *block, int *smem_bytes, int 
     if (!c) return fail(TOFRT_E_BADARG, "tofrt_kernel_info: ctx is NULL");
     cudaFuncAttributes fa{};
     CUDA_TRY(cudaFuncGetAttributes(&fa, tofrt_table_kernel));
-    if (grid) *grid = c->sm_count;
+    if (grid) *grid = c->sm_count * c->ctas_per_sm;
     if (block) *block = kThreads;
     if (smem_bytes) *smem_bytes = (int)c->smem;
     if (regs) *regs = fa.numRegs;

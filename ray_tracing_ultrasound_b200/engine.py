@@ -70,6 +70,23 @@ class TofEngine:
         self.K, self.E = len(alpha), len(x_rx)
         return self
 
+    def set_search(self, mode):
+        """'guided' (default) or 'scan' (the reference's literal O(N) search); same results."""
+        value = {"scan": 0, "guided": 1}[mode]
+        _capi.check(self._lib.tofrt_set_option(self._ctx, 1, value))
+        return self
+
+    @property
+    def lens_shape(self):
+        """+1 concave, -1 convex, 0 neither (guided search falls back to the scan)."""
+        return self._lib.tofrt_get_info(self._ctx, 1)
+
+    def last_stats(self):
+        """Search statistics of the last table call (see tofrt_last_stats)."""
+        arr = (ctypes.c_ulonglong * 4)()
+        _capi.check(self._lib.tofrt_last_stats(self._ctx, arr))
+        return dict(zip(("rays", "scan_rays", "scan_groups", "on_sample_rays"), (int(x) for x in arr)))
+
     def lens(self):
         """lens_1_x, lens_1_z (main_rt.py:338)."""
         x, z = np.empty(self.K), np.empty(self.K)

@@ -230,3 +230,71 @@ def test_full_size_grid_properties(engine, oracle_dm):
     t2 = engine.tof_table_cuda(r_d[lo:hi].contiguous(), o_d[lo:hi].contiguous())
     torch.cuda.synchronize()
     assert torch.equal(t2.tof, tof[lo:hi]) and torch.equal(t2.k_hit, k_hit[lo:hi])
+
+
+def _table_all(engine, radii, offsets):
+    t = engine.tof_table(radii, offsets, records=("idx", "target_x", "lens2_x", "lens2_z"))
+    return t
+
+
+@pytest.mark.parametrize("case", ["sweep", "random", "grazing", "compare", "convex"])
+def test_guided_search_equals_literal_scan(engine, oracle_dm, case):
+    """TOFRT_SEARCH_GUIDED must return exactly what the reference's O(N) scan returns."""
+    x_a, z_a = rs.transducer()
+    kw = {}
+    n_alpha = rs.NUM_ALPHA_POINTS_RT
+    rng = np.random.default_rng(11)
+    if case == "sweep":
+        radii, offsets = rs.sweep_grid()  # includes the 12 degenerate geometries (line through a sample)
+    elif case == "random":
+        radii, offsets = rng.uniform(0.003, 0.15, 2000), rng.uniform(-0.03, 0.03, 2000)
+    elif case == "grazing":
+        # pipes that reach into / touch the lens: tangent and multiply-crossing return paths
+        radii = rng.uniform(0.07, 0.12, 1500)
+        offsets = rng.uniform(-0.05, 0.05, 1500)
+    elif case == "compare":
+        n_alpha = rs.NUM_ALPHA_POINTS_COMPARE
+        radii, offsets = np.array([0.037, 0.05, 0.02]), np.array([0.0038, 0.0, -0.009])
+    else:  # a parameter set (unphysical: l0 < 0) whose sampled surface is a CONVEX polyline
+        kw = dict(c1=1986.5, c2=3134.7, l0=-0.20058, h0=0.04446)
+        radii, offsets = rng.uniform(0.01, 0.12, 500), rng.uniform(-0.01, 0.01, 500)
+    alpha, zf = rs.launch_angles(n_alpha), rs.focus_line(n_alpha)
+    z_sh = z_a[32]
+    if case == "convex":
+        alpha = np.linspace(-0.3326, 0.3326, 400)
+        z_sh = float(np.float64(kw["l0"]) + np.float64(kw["h0"]))
+        zf = np.ones(400) * z_sh
+    engine.setup(alpha, zf, x_a[32], z_sh, x_a, **kw)
+    assert engine.lens_shape == (-1 if case == "convex" else 1)
+    engine.set_search("scan")
+    a = _table_all(engine, radii, offsets)
+    engine.set_search("guided")
+    b = _table_all(engine, radii, offsets)
+    assert np.array_equal(a.records["idx"], b.records["idx"])
+    assert np.array_equal(a.k_hit, b.k_hit) and np.array_equal(a.tof, b.tof)
+    for key in ("target_x", "lens2_x", "lens2_z"):
+        assert _same(a.records[key], b.records[key]), key
+    # and both equal the oracle twin
+    p = oracle_dm.params(**kw)
+    tof, k_hit, idx = oracle_dm.table(p, radii, offsets, x_a[32], z_sh, zf, alpha, x_a, want_idx=True)
+    assert np.array_equal(b.records["idx"], idx)
+    assert np.array_equal(b.k_hit, k_hit.T) and np.array_equal(b.tof, tof.T)
+    assert (idx >= 0).mean() > 0.2  # the case really exercises the search
+
+
+def test_non_monotone_lens_disables_guided_search(engine, oracle_dm):
+    """A launch-angle list that is not increasing gives a lens polyline that is neither
+    concave nor convex: the engine must notice and use the literal scan."""
+    x_a, z_a = rs.transducer()
+    alpha = rs.launch_angles(200).copy()
+    rng = np.random.default_rng(3)
+    rng.shuffle(alpha)
+    zf = rs.focus_line(200)
+    engine.setup(alpha, zf, x_a[32], z_a[32], x_a)
+    assert engine.lens_shape == 0
+    radii, offsets = rng.uniform(0.01, 0.1, 50), rng.uniform(-0.01, 0.01, 50)
+    t = engine.tof_table(radii, offsets, records=("idx",))
+    p = oracle_dm.params()
+    tof, k_hit, idx = oracle_dm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a, want_idx=True)
+    assert np.array_equal(t.records["idx"], idx)
+    assert np.array_equal(t.k_hit, k_hit.T) and np.array_equal(t.tof, tof.T)
