@@ -12,10 +12,15 @@
  * np.arctan/np.arctan2/np.arcsin, call sites main_rt.py:184-405); they differ
  * from these by <= ~2 ulp, i.e. <= 1e-19 s on a travel time.
  *
- * Accuracy (tests/test_math.py, against mpmath): <= 2 ulp on the engine's
- * argument ranges.  Domain of the trigonometric reduction: |x| < 2^30 (angles
- * in this engine never leave [-4 pi, 4 pi]); larger finite arguments return
- * NaN instead of a value with no correct digits.
+ * Written for the GPU first: straight-line code (selects, no data-dependent
+ * branches, so 32 rays stay converged), one division per function, and the
+ * polynomial coefficients live in constant memory on the device so that each
+ * Horner step is a single DFMA with a c[bank][offset] operand.
+ *
+ * Accuracy (tests/test_math.py, against mpmath): sin, cos < 1 ulp; tan, atan,
+ * atan2 < 2.5 ulp; asin < 3 ulp.  Domain of the trigonometric reduction:
+ * |x| < 2^30 (angles in this engine never leave [-4 pi, 4 pi]); larger finite
+ * arguments return NaN instead of a value with no correct digits.
  *
  * Compile without floating-point contraction (nvcc -fmad=false,
  * gcc -ffp-contract=off): every fused operation below is an explicit fma().
@@ -24,168 +29,161 @@
 #define TOFRT_MATH_H
 
 #include <math.h>
+#include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
-#define TOFRT_HD __host__ __device__ __forceinline__
+#define TOFRT_HD __device__ __forceinline__
+#define TOFRT_TABLE static __constant__ double
 #else
 #define TOFRT_HD static inline
+#define TOFRT_TABLE static const double
 #endif
 
-#define TOFRT_PIO2_HI 1.5707963267948966     /* 0x1.921fb54442d18p+0  */
-#define TOFRT_PIO2_MID 6.123233995736766e-17 /* 0x1.1a62633145c07p-54 */
-#define TOFRT_PIO2_LO -1.4973849048591698e-33
-#define TOFRT_TWO_OVER_PI 0.6366197723675814
-#define TOFRT_PI_HI 3.141592653589793
-#define TOFRT_PI_LO 1.2246467991473532e-16
-#define TOFRT_PIO4_HI 0.7853981633974483
-#define TOFRT_PIO4_LO 3.061616997868383e-17
-#define TOFRT_ATAN_HALF_HI 0.4636476090008061 /* atan(1/2) */
-#define TOFRT_ATAN_HALF_LO 2.2698777452961687e-17
+/* One table for every constant; indices below.  (gcc folds tofrt_k[IDX] into
+ * the literal; nvcc turns it into a constant-bank operand.) */
+enum {
+    TK_PIO2_HI, TK_PIO2_MID, TK_PIO2_LO, TK_TWO_OVER_PI, TK_MAGIC, TK_PI_HI, TK_PI_LO, TK_PIO4_HI, TK_PIO4_LO,
+    TK_S1, TK_S2, TK_S3, TK_S4, TK_S5, TK_S6,
+    TK_C1, TK_C2, TK_C3, TK_C4, TK_C5, TK_C6,
+    TK_A0, TK_A1, TK_A2, TK_A3, TK_A4, TK_A5, TK_A6, TK_A7, TK_A8, TK_A9, TK_A10,
+    TK_COUNT
+};
+TOFRT_TABLE tofrt_k[TK_COUNT] = {
+    1.5707963267948966,      /* PIO2_HI  0x1.921fb54442d18p+0  */
+    6.123233995736766e-17,   /* PIO2_MID 0x1.1a62633145c07p-54 */
+    -1.4973849048591698e-33, /* PIO2_LO                        */
+    0.6366197723675814,      /* 2/pi                           */
+    6755399441055744.0,      /* 1.5 * 2^52: round to nearest integer */
+    3.141592653589793, 1.2246467991473532e-16, /* pi hi, lo    */
+    0.7853981633974483, 3.061616997868383e-17, /* pi/4 hi, lo  */
+    /* sin(x) = x + x^3 (S1 + x^2 (S2 + ...)) on [-pi/4, pi/4] */
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    /* cos(x) = 1 - x^2/2 + x^4 (C1 + x^2 (C2 + ...)) */
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,
+    /* atan(u) = u - u^3 (A0 + u^2 (A1 + ...)) on [-7/16, 7/16] */
+    3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01,
+    -1.11111104054623557880e-01, 9.09088713343650656196e-02, -7.69187620504482999495e-02,
+    6.66107313738753120669e-02, -5.83357013379057348645e-02, 4.97687799461593236017e-02,
+    -3.65315727442169155270e-02, 1.62858201153657823623e-02,
+};
+#define TK(name) tofrt_k[TK_##name]
 
-/* x = n*(pi/2) + (r + rl), |r| <= pi/4 (+ a few ulp); returns n mod 4 in *q.
- * Three-term Cody-Waite with an exact first step (fma) and a double-double
- * remainder, so the result keeps full relative accuracy near multiples of pi/2. */
-TOFRT_HD void tofrt_reduce_pio2(double x, double *r, double *rl, int *q)
+/* low 32 bits of a double's representation */
+TOFRT_HD uint32_t tofrt_lo32(double v)
 {
-    const double magic = 6755399441055744.0; /* 1.5 * 2^52: round to nearest integer */
-    double n = fma(x, TOFRT_TWO_OVER_PI, magic) - magic;
-    double r1 = fma(-n, TOFRT_PIO2_HI, x); /* exact */
-    double ph = n * TOFRT_PIO2_MID;
-    double pl = fma(n, TOFRT_PIO2_MID, -ph); /* ph + pl = n * MID exactly */
-    double s = r1 - ph;                      /* two-sum of r1 + (-ph) */
-    double bb = s - r1;
-    double e = (r1 - (s - bb)) + (-ph - bb);
-    *r = s;
-    *rl = fma(-n, TOFRT_PIO2_LO, e - pl);
-    *q = (int)((long long)n & 3);
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(v);
+#else
+    uint64_t u;
+    memcpy(&u, &v, sizeof u);
+    return (uint32_t)u;
+#endif
 }
 
-/* sin(x + y) for |x| <= pi/4, y the tail of x */
-TOFRT_HD double tofrt_sin_kernel(double x, double y)
+/* sin and cos of (x + y) for |x| <= pi/4 (+ a few ulp), y the tail of x */
+TOFRT_HD void tofrt_sincos_kernel(double x, double y, double *sn, double *cs)
 {
-    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
-                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
-                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
     double z = x * x;
-    double r = fma(z, fma(z, fma(z, fma(z, S6, S5), S4), S3), S2);
+    /* sin */
+    double rs = fma(z, fma(z, fma(z, fma(z, TK(S6), TK(S5)), TK(S4)), TK(S3)), TK(S2));
     double v = z * x;
-    return x - ((z * (0.5 * y - v * r) - y) - v * S1);
-}
-
-/* cos(x + y) for |x| <= pi/4 */
-TOFRT_HD double tofrt_cos_kernel(double x, double y)
-{
-    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
-                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
-                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
-    double z = x * x;
-    double r = z * fma(z, fma(z, fma(z, fma(z, fma(z, C6, C5), C4), C3), C2), C1);
+    *sn = x - ((z * (0.5 * y - v * rs) - y) - v * TK(S1));
+    /* cos */
+    double rc = z * fma(z, fma(z, fma(z, fma(z, fma(z, TK(C6), TK(C5)), TK(C4)), TK(C3)), TK(C2)), TK(C1));
     double hz = 0.5 * z;
     double w = 1.0 - hz;
-    return w + (((1.0 - w) - hz) + (z * r - x * y));
+    *cs = w + (((1.0 - w) - hz) + (z * rc - x * y));
+}
+
+/* Quadrant-reduced sine and cosine: x = n*(pi/2) + (r + rl) by a three-term
+ * Cody-Waite reduction whose first step is exact (fma) and whose remainder is
+ * kept as a double-double, so the result keeps full relative accuracy near
+ * multiples of pi/2.  Returns sin(r + rl), cos(r + rl) and n mod 4. */
+TOFRT_HD int tofrt_sincos_reduced(double x, double *s, double *c)
+{
+    double t = fma(x, TK(TWO_OVER_PI), TK(MAGIC));
+    double n = t - TK(MAGIC);
+    double r1 = fma(-n, TK(PIO2_HI), x); /* exact */
+    double ph = n * TK(PIO2_MID);
+    double pl = fma(n, TK(PIO2_MID), -ph); /* ph + pl = n * MID exactly */
+    double r = r1 - ph;                    /* two-sum of r1 + (-ph) */
+    double bb = r - r1;
+    double e = (r1 - (r - bb)) + (-ph - bb);
+    double rl = fma(-n, TK(PIO2_LO), e - pl);
+    tofrt_sincos_kernel(r, rl, s, c);
+    return (int)(tofrt_lo32(t) & 3u); /* the magic constant leaves n in the low mantissa bits */
+}
+
+/* sine and cosine; NaN for NaN, infinities and |x| >= 2^30 */
+TOFRT_HD void tofrt_sincos(double x, double *sn, double *cs)
+{
+    double s, c;
+    int q = tofrt_sincos_reduced(x, &s, &c);
+    double vs = (q & 1) ? c : s, vc = (q & 1) ? s : c;
+    vs = (q & 2) ? -vs : vs;
+    vc = ((q + 1) & 2) ? -vc : vc;
+    int ok = fabs(x) < 1073741824.0;
+    *sn = ok ? vs : NAN;
+    *cs = ok ? vc : NAN;
 }
 
 TOFRT_HD double tofrt_sin(double x)
 {
-    if (!(fabs(x) < 1073741824.0)) return x - x + NAN; /* NaN, inf, out of domain */
-    double r, rl;
-    int q;
-    tofrt_reduce_pio2(x, &r, &rl, &q);
-    double v = (q & 1) ? tofrt_cos_kernel(r, rl) : tofrt_sin_kernel(r, rl);
-    return (q & 2) ? -v : v;
+    double s, c;
+    tofrt_sincos(x, &s, &c);
+    return s;
 }
 
 TOFRT_HD double tofrt_cos(double x)
 {
-    if (!(fabs(x) < 1073741824.0)) return x - x + NAN;
-    double r, rl;
-    int q;
-    tofrt_reduce_pio2(x, &r, &rl, &q);
-    double v = (q & 1) ? tofrt_sin_kernel(r, rl) : tofrt_cos_kernel(r, rl);
-    return ((q + 1) & 2) ? -v : v;
+    double s, c;
+    tofrt_sincos(x, &s, &c);
+    return c;
 }
 
-/* both at once; bit-identical to tofrt_sin / tofrt_cos */
-TOFRT_HD void tofrt_sincos(double x, double *sn, double *cs)
-{
-    if (!(fabs(x) < 1073741824.0)) { *sn = *cs = x - x + NAN; return; }
-    double r, rl;
-    int q;
-    tofrt_reduce_pio2(x, &r, &rl, &q);
-    double s = tofrt_sin_kernel(r, rl), c = tofrt_cos_kernel(r, rl);
-    double vs = (q & 1) ? c : s, vc = (q & 1) ? s : c;
-    *sn = (q & 2) ? -vs : vs;
-    *cs = ((q + 1) & 2) ? -vc : vc;
-}
-
-/* tan = sin/cos on the reduced argument (one division) */
+/* tan = sin/cos of the reduced argument (one division) */
 TOFRT_HD double tofrt_tan(double x)
 {
-    if (!(fabs(x) < 1073741824.0)) return x - x + NAN;
-    double r, rl;
-    int q;
-    tofrt_reduce_pio2(x, &r, &rl, &q);
-    double s = tofrt_sin_kernel(r, rl), c = tofrt_cos_kernel(r, rl);
-    return (q & 1) ? (-c) / s : s / c;
+    double s, c;
+    int q = tofrt_sincos_reduced(x, &s, &c);
+    double num = (q & 1) ? -c : s, den = (q & 1) ? s : c;
+    double v = num / den;
+    return (fabs(x) < 1073741824.0) ? v : NAN;
 }
 
-/* atan(a/b) for 0 <= a <= b, result in [0, pi/4].  The argument is brought
- * into the polynomial's interval with the classic breakpoints 7/16, 11/16
- * applied to numerator and denominator, so there is a single division. */
-TOFRT_HD double tofrt_atan_core(double a, double b)
+/* atan2 with a single division.  With a = min(|x|,|y|), b = max(|x|,|y|):
+ * atan(a/b) = atan(u) for u = a/b when a < 7/16 b, else pi/4 + atan(u) with
+ * u = (a-b)/(a+b) in (-0.392, 0]; then the octant is undone with hi/lo splits
+ * of pi/2 and pi. */
+TOFRT_HD double tofrt_atan2(double y, double x)
 {
-    const double aT0 = 3.33333333333329318027e-01, aT1 = -1.99999999998764832476e-01,
-                 aT2 = 1.42857142725034663711e-01, aT3 = -1.11111104054623557880e-01,
-                 aT4 = 9.09088713343650656196e-02, aT5 = -7.69187620504482999495e-02,
-                 aT6 = 6.66107313738753120669e-02, aT7 = -5.83357013379057348645e-02,
-                 aT8 = 4.97687799461593236017e-02, aT9 = -3.65315727442169155270e-02,
-                 aT10 = 1.62858201153657823623e-02;
-    double num, den, hi, lo;
-    if (a < 0.4375 * b) {
-        num = a; den = b; hi = 0.0; lo = 0.0;
-    } else if (a < 0.6875 * b) {
-        num = 2.0 * a - b; den = 2.0 * b + a; hi = TOFRT_ATAN_HALF_HI; lo = TOFRT_ATAN_HALF_LO;
-    } else {
-        num = a - b; den = a + b; hi = TOFRT_PIO4_HI; lo = TOFRT_PIO4_LO;
-    }
+    double ax = fabs(x), ay = fabs(y);
+    int swap = ay > ax;
+    double a = swap ? ax : ay, b = swap ? ay : ax; /* NaN stays NaN through the arithmetic below */
+    int small = a < 0.4375 * b;
+    double num = small ? a : a - b;
+    double den = small ? b : a + b;
     double u = num / den;
     double z = u * u;
     double w = z * z;
-    double s1 = z * fma(w, fma(w, fma(w, fma(w, fma(w, aT10, aT8), aT6), aT4), aT2), aT0);
-    double s2 = w * fma(w, fma(w, fma(w, fma(w, aT9, aT7), aT5), aT3), aT1);
-    return hi - ((u * (s1 + s2) - lo) - u);
-}
-
-TOFRT_HD double tofrt_atan2(double y, double x)
-{
-    if (x != x || y != y) return x + y;
-    double ax = fabs(x), ay = fabs(y);
-    int swap = ay > ax;
-    double a = swap ? ax : ay, b = swap ? ay : ax;
-    double r;
-    if (b == 0.0) r = 0.0;                      /* atan2(+-0, +-0) */
-    else if (a == INFINITY) r = TOFRT_PIO4_HI;  /* both infinite */
-    else r = tofrt_atan_core(a, b);
-    if (swap) r = TOFRT_PIO2_HI - (r - TOFRT_PIO2_MID);
-    if (signbit(x)) r = TOFRT_PI_HI - (r - TOFRT_PI_LO);
+    double s1 = z * fma(w, fma(w, fma(w, fma(w, fma(w, TK(A10), TK(A8)), TK(A6)), TK(A4)), TK(A2)), TK(A0));
+    double s2 = w * fma(w, fma(w, fma(w, fma(w, TK(A9), TK(A7)), TK(A5)), TK(A3)), TK(A1));
+    double us = u * (s1 + s2);
+    double r = small ? u - us : TK(PIO4_HI) - ((us - TK(PIO4_LO)) - u);
+    r = (b == 0.0) ? 0.0 : r;             /* atan2(+-0, +-0): 0/0 above */
+    r = (a == INFINITY && b == INFINITY) ? TK(PIO4_HI) : r; /* both infinite: inf/inf above */
+    r = swap ? TK(PIO2_HI) - (r - TK(PIO2_MID)) : r;
+    r = signbit(x) ? TK(PI_HI) - (r - TK(PI_LO)) : r;
     return copysign(r, y);
 }
 
-TOFRT_HD double tofrt_atan(double x)
-{
-    if (x != x) return x;
-    double ax = fabs(x);
-    int swap = ax > 1.0;
-    double r = swap ? tofrt_atan_core(1.0, ax) : tofrt_atan_core(ax, 1.0);
-    if (swap) r = TOFRT_PIO2_HI - (r - TOFRT_PIO2_MID);
-    return copysign(r, x);
-}
+TOFRT_HD double tofrt_atan(double x) { return tofrt_atan2(x, 1.0); }
 
 /* asin(x) = atan2(x, sqrt((1 - x)(1 + x))); NaN for |x| > 1 (total internal
  * reflection in main_rt.py:277) */
-TOFRT_HD double tofrt_asin(double x)
-{
-    return tofrt_atan2(x, sqrt((1.0 - x) * (1.0 + x)));
-}
+TOFRT_HD double tofrt_asin(double x) { return tofrt_atan2(x, sqrt((1.0 - x) * (1.0 + x))); }
 
 #endif /* TOFRT_MATH_H */
