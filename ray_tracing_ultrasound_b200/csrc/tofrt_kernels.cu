@@ -580,6 +580,12 @@ struct tofrt_ctx {
     double *d_xrx = nullptr, *d_xs = nullptr;
     int *d_perm = nullptr, *d_bad = nullptr;
     unsigned long long *d_counter = nullptr;
+    // host-buffer pipeline (tofrt_table_host)
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    void *ws[2] = {nullptr, nullptr};
+    size_t ws_bytes = 0, in_cap = 0;
+    double *d_in = nullptr;
     void free_all()
     {
         cudaFree(d_alpha); cudaFree(d_zf); cudaFree(d_a); cudaFree(d_b); cudaFree(d_phi); cudaFree(d_leg1);
@@ -625,6 +631,13 @@ int tofrt_destroy(tofrt_ctx *c)
     cudaSetDevice(c->device);
     c->free_all();
     cudaFree(c->d_counter);
+    cudaFree(c->ws[0]); cudaFree(c->ws[1]); cudaFree(c->d_in);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+        if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
+    }
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
     delete c;
     return TOFRT_OK;
 }
@@ -815,6 +828,11 @@ int tofrt_table_dev(tofrt_ctx *c, const double *d_radius, const double *d_offset
     return TOFRT_OK;
 }
 
+// Host-buffer path: the geometries are cut into chunks whose outputs are ~128 MB; chunk i is
+// traced on one stream into one of two device slots while the results of chunk i-1 travel to the
+// host on a second stream (pinned host buffers make that copy truly asynchronous), so the
+// end-to-end time is max(compute, PCIe) instead of their sum.  The workspace is owned by the
+// context and only ever grows.
 int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, long long G, double *tof,
                      int *k_hit, const tofrt_ray_records *rec)
 {
@@ -824,51 +842,86 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
     if (!radius || !offset || !tof || !k_hit) return fail(TOFRT_E_BADARG, "tofrt_table_host: NULL buffer");
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t K = c->K, E = c->E, g = (size_t)G;
-    double *d_in = nullptr, *d_tof = nullptr;
-    int *d_kh = nullptr;
-    std::vector<void *> owned;
-    auto cleanup = [&]() { for (void *q : owned) cudaFree(q); };
-    auto dalloc = [&](void **q, size_t bytes) {
-        cudaError_t e = cudaMalloc(q, bytes);
-        if (e == cudaSuccess) owned.push_back(*q);
-        return e;
-    };
-#define TRY_C(expr)                                                                                   \
-    do {                                                                                              \
-        cudaError_t e_ = (expr);                                                                      \
-        if (e_ != cudaSuccess) { cleanup(); return fail(TOFRT_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } \
-    } while (0)
-    TRY_C(dalloc((void **)&d_in, sizeof(double) * 2 * g));
-    TRY_C(dalloc((void **)&d_tof, sizeof(double) * g * E));
-    TRY_C(dalloc((void **)&d_kh, sizeof(int) * g * E));
-    TRY_C(cudaMemcpy(d_in, radius, sizeof(double) * g, cudaMemcpyHostToDevice));
-    TRY_C(cudaMemcpy(d_in + g, offset, sizeof(double) * g, cudaMemcpyHostToDevice));
-    tofrt_ray_records drec{};
-    if (rec) {
-        if (rec->pipe_x) TRY_C(dalloc((void **)&drec.pipe_x, sizeof(double) * g * K));
-        if (rec->pipe_z) TRY_C(dalloc((void **)&drec.pipe_z, sizeof(double) * g * K));
-        if (rec->lens2_x) TRY_C(dalloc((void **)&drec.lens2_x, sizeof(double) * g * K));
-        if (rec->lens2_z) TRY_C(dalloc((void **)&drec.lens2_z, sizeof(double) * g * K));
-        if (rec->target_x) TRY_C(dalloc((void **)&drec.target_x, sizeof(double) * g * K));
-        if (rec->idx) TRY_C(dalloc((void **)&drec.idx, sizeof(int) * g * K));
-        if (rec->legs) TRY_C(dalloc((void **)&drec.legs, sizeof(double) * g * K * 4));
+    tofrt_ray_records none{};
+    const tofrt_ray_records &R = rec ? *rec : none;
+    // bytes of output per geometry, each array 256-byte aligned inside a slot
+    size_t per_geom = E * (sizeof(double) + sizeof(int));
+    const int n_rec_d = (R.pipe_x != nullptr) + (R.pipe_z != nullptr) + (R.lens2_x != nullptr) +
+                        (R.lens2_z != nullptr) + (R.target_x != nullptr) + 4 * (R.legs != nullptr);
+    per_geom += (size_t)n_rec_d * K * sizeof(double) + (R.idx ? K * sizeof(int) : 0);
+    size_t chunk = std::max<size_t>(1, ((size_t)128 << 20) / per_geom);
+    chunk = std::min(chunk, g);
+    if (g > chunk) {  // even chunks, each a multiple of 1024 geometries
+        size_t n = (g + chunk - 1) / chunk;
+        chunk = (((g + n - 1) / n) + 1023) / 1024 * 1024;
     }
-    int rc = tofrt_table_dev(c, d_in, d_in + g, G, d_tof, d_kh, rec ? &drec : nullptr, nullptr);
-    if (rc != TOFRT_OK) { cleanup(); return rc; }
-    TRY_C(cudaMemcpy(tof, d_tof, sizeof(double) * g * E, cudaMemcpyDeviceToHost));
-    TRY_C(cudaMemcpy(k_hit, d_kh, sizeof(int) * g * E, cudaMemcpyDeviceToHost));
-    if (rec) {
-        if (rec->pipe_x) TRY_C(cudaMemcpy(rec->pipe_x, drec.pipe_x, sizeof(double) * g * K, cudaMemcpyDeviceToHost));
-        if (rec->pipe_z) TRY_C(cudaMemcpy(rec->pipe_z, drec.pipe_z, sizeof(double) * g * K, cudaMemcpyDeviceToHost));
-        if (rec->lens2_x) TRY_C(cudaMemcpy(rec->lens2_x, drec.lens2_x, sizeof(double) * g * K, cudaMemcpyDeviceToHost));
-        if (rec->lens2_z) TRY_C(cudaMemcpy(rec->lens2_z, drec.lens2_z, sizeof(double) * g * K, cudaMemcpyDeviceToHost));
-        if (rec->target_x) TRY_C(cudaMemcpy(rec->target_x, drec.target_x, sizeof(double) * g * K, cudaMemcpyDeviceToHost));
-        if (rec->idx) TRY_C(cudaMemcpy(rec->idx, drec.idx, sizeof(int) * g * K, cudaMemcpyDeviceToHost));
-        if (rec->legs) TRY_C(cudaMemcpy(rec->legs, drec.legs, sizeof(double) * g * K * 4, cudaMemcpyDeviceToHost));
+    const size_t slot_bytes = chunk * per_geom + 16 * 256;
+
+    // grow-only workspace
+    if (!c->s_compute) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        }
     }
-    TRY_C(cudaDeviceSynchronize());
-    cleanup();
-#undef TRY_C
+    if (c->ws_bytes < slot_bytes) {
+        for (int i = 0; i < 2; ++i) { cudaFree(c->ws[i]); c->ws[i] = nullptr; }
+        c->ws_bytes = 0;
+        for (int i = 0; i < 2; ++i) CUDA_TRY(cudaMalloc(&c->ws[i], slot_bytes));
+        c->ws_bytes = slot_bytes;
+    }
+    if (c->in_cap < 2 * g) {
+        cudaFree(c->d_in); c->d_in = nullptr; c->in_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->d_in, sizeof(double) * 2 * g));
+        c->in_cap = 2 * g;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_in, radius, sizeof(double) * g, cudaMemcpyHostToDevice, c->s_compute));
+    CUDA_TRY(cudaMemcpyAsync(c->d_in + g, offset, sizeof(double) * g, cudaMemcpyHostToDevice, c->s_compute));
+
+    int rc = TOFRT_OK;
+    size_t done = 0;
+    for (int i = 0; done < g && rc == TOFRT_OK; ++i, done += chunk) {
+        const int slot = i & 1;
+        const size_t n = std::min(chunk, g - done);
+        // carve the slot
+        char *base = (char *)c->ws[slot];
+        auto take = [&](size_t bytes) { char *q = base; base += (bytes + 255) / 256 * 256; return q; };
+        double *d_tof = (double *)take(n * E * sizeof(double));
+        int *d_kh = (int *)take(n * E * sizeof(int));
+        tofrt_ray_records d{};
+        if (R.pipe_x) d.pipe_x = (double *)take(n * K * sizeof(double));
+        if (R.pipe_z) d.pipe_z = (double *)take(n * K * sizeof(double));
+        if (R.lens2_x) d.lens2_x = (double *)take(n * K * sizeof(double));
+        if (R.lens2_z) d.lens2_z = (double *)take(n * K * sizeof(double));
+        if (R.target_x) d.target_x = (double *)take(n * K * sizeof(double));
+        if (R.idx) d.idx = (int *)take(n * K * sizeof(int));
+        if (R.legs) d.legs = (double *)take(n * K * 4 * sizeof(double));
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_free[slot], 0));
+        rc = tofrt_table_dev(c, c->d_in + done, c->d_in + g + done, (long long)n, d_tof, d_kh, rec ? &d : nullptr,
+                             (void *)c->s_compute);
+        if (rc != TOFRT_OK) break;
+        CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->s_compute));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_copy, c->ev_done[slot], 0));
+        auto back = [&](void *dst, const void *src, size_t bytes) {
+            return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->s_copy);
+        };
+        CUDA_TRY(back(tof + done * E, d_tof, n * E * sizeof(double)));
+        CUDA_TRY(back(k_hit + done * E, d_kh, n * E * sizeof(int)));
+        if (R.pipe_x) CUDA_TRY(back(R.pipe_x + done * K, d.pipe_x, n * K * sizeof(double)));
+        if (R.pipe_z) CUDA_TRY(back(R.pipe_z + done * K, d.pipe_z, n * K * sizeof(double)));
+        if (R.lens2_x) CUDA_TRY(back(R.lens2_x + done * K, d.lens2_x, n * K * sizeof(double)));
+        if (R.lens2_z) CUDA_TRY(back(R.lens2_z + done * K, d.lens2_z, n * K * sizeof(double)));
+        if (R.target_x) CUDA_TRY(back(R.target_x + done * K, d.target_x, n * K * sizeof(double)));
+        if (R.idx) CUDA_TRY(back(R.idx + done * K, d.idx, n * K * sizeof(int)));
+        if (R.legs) CUDA_TRY(back(R.legs + done * K * 4, d.legs, n * K * 4 * sizeof(double)));
+        CUDA_TRY(cudaEventRecord(c->ev_free[slot], c->s_copy));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c->s_compute), e2 = cudaStreamSynchronize(c->s_copy);
+    if (rc != TOFRT_OK) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(TOFRT_E_CUDA, std::string("tofrt_table_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     return TOFRT_OK;
 }
 
