@@ -1,0 +1,61 @@
+"""CPU, world_size 2, gloo: the host-side sharding logic (bounds, shard -> gather round trip).
+The table rows here come from the oracle (the CUDA path needs a GPU); what is tested is that a
+sharded table gathered back equals the unsharded one, bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ray_tracing_ultrasound_b200 import reference_setup as rs, sharding
+
+
+def test_shard_bounds_cover_everything():
+    for G in (0, 1, 5, 210, 1025):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_bounds(G, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == G
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(10, 2, 2)
+
+
+def _worker(rank, world, port, G, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import Oracle
+    o = Oracle(device_math=True)
+    p = o.params()
+    x_a, z_a = rs.transducer()
+    alpha, zf = rs.launch_angles(200), rs.focus_line(200)
+    radii, offsets = rs.synthetic_grid(G, 1)
+    r_s, o_s = sharding.shard_geometries(radii, offsets, world, rank)
+    tof, k_hit, _ = o.table(p, r_s, o_s, x_a[32], z_a[32], zf, alpha, x_a)
+    tof_full, k_full = sharding.gather_table(torch.from_numpy(np.ascontiguousarray(tof.T)),
+                                             torch.from_numpy(np.ascontiguousarray(k_hit.T)), G)
+    if rank == 0:
+        tof1, k1, _ = o.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a)
+        ok = np.array_equal(tof_full.numpy(), tof1.T) and np.array_equal(k_full.numpy(), k1.T)
+        out.put(bool(ok) and tof_full.shape == (G, len(x_a)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("G", [8, 7])
+def test_shard_gather_roundtrip_gloo_world2(G):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, G, out)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(120)
+        assert pr.exitcode == 0
+    assert out.get() is True
