@@ -36,7 +36,8 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of tofrt_table_kernel from the committed
 # `ncu --set full` captures (profiles/), scaled to the full 1024x1024 grid; None until captured.
-NCU_TRAFFIC_BYTES = {"guided": None, "scan": None}
+# profiles/ncu_r1_table_kernel.json: 150.7 MB (guided) / 152.2 MB (scan) per 131 072-geometry launch
+NCU_TRAFFIC_BYTES = {"guided": 150.7e6 * 8, "scan": 152.2e6 * 8}
 
 METRIC = "ray-solves/sec (element x pixel)"
 UNIT = "ray-solves/s"
@@ -149,6 +150,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=GRID_R, help="radii per GPU (default 1024; offsets stay 1024)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", action="store_true",
+                    help="after timing, all-gather the table shards over NCCL and check them (N > 1)")
     ap.add_argument("--search", default="guided", choices=["guided", "scan"],
                     help="return-path search of the timed steps (identical results; see include/tofrt.h)")
     args = ap.parse_args()
@@ -250,6 +253,24 @@ def main():
     del tof_o, kh_o
     eng.set_search(args.search)
 
+    gather_info = None
+    if args.gather and world > 1:
+        from ray_tracing_ultrasound_b200 import sharding
+        rows = min(G, 65536)  # a bounded slice per rank keeps the gathered table small
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        g0.record()
+        tof_all, kh_all = sharding.gather_table(tof_d[:rows], kh_d[:rows], rows * world)
+        g1.record()
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(tof_all[rank * rows:(rank + 1) * rows], tof_d[:rows]) and
+                  torch.equal(kh_all[rank * rows:(rank + 1) * rows], kh_d[:rows]) and
+                  tof_all.shape[0] == rows * world)
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        gather_info = {"rows_per_rank": rows, "bytes_gathered_per_rank": int(rows * world * E * 12),
+                       "ms": g0.elapsed_time(g1), "ok": bool(okt.item())}
+
     if rank == 0:
         peak_fma, peak_issue = eng.measure_fp64_peak()
         info = eng.kernel_info()
@@ -297,6 +318,8 @@ def main():
             "gpu_launches": args.steps * 1,
             "roofline": roofline,
         }
+        if gather_info:
+            out["all_gather"] = gather_info
         if not args.no_cpu:
             v, threads, n, dt = cpu_port_rate(x_a, z_a, alpha, zf, radii, offsets)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
