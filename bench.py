@@ -253,6 +253,33 @@ def main():
     del tof_o, kh_o
     eng.set_search(args.search)
 
+    # ---- FP32 mode, reported separately (north_star): time and measured error vs FP64 ----
+    tof32 = torch.empty((G, E), dtype=torch.float32, device=dev)
+    kh32 = torch.empty((G, E), dtype=torch.int32, device=dev)
+    eng.tof_table_f32_cuda(r_d, o_d, out_tof=tof32, out_k_hit=kh32)
+    barrier()
+    ef = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ef[0].record()
+    for _ in range(2):
+        eng.tof_table_f32_cuda(r_d, o_d, out_tof=tof32, out_k_hit=kh32)
+    ef[1].record()
+    barrier()
+    f32_ms = ef[0].elapsed_time(ef[1]) / 2
+    h64, h32 = kh_d >= 0, kh32 >= 0
+    both = h64 & h32
+    same_ray = both & (kh_d == kh32)
+    dts = (tof32.double() - tof_d)[same_ray].abs()
+    fp32_info = {
+        "value": E * G / (f32_ms * 1e-3), "unit": UNIT + " per GPU", "kernel_ms": f32_ms,
+        "max_abs_dt_same_ray_s": float(dts.max()), "median_abs_dt_same_ray_s": float(dts.median()),
+        "max_abs_dt_common_hits_s": float((tof32.double() - tof_d)[both].abs().max()),
+        "hit_flag_mismatch_frac": float((h64 != h32).float().mean()),
+        "first_ray_mismatch_frac_of_common_hits": float(1.0 - same_ray.sum().double() / both.sum().double()),
+        "note": "per-ray arithmetic in float32 (tables rounded from FP64); landing points move by ~5e-7 m, so hit "
+                "decisions at atol = 1e-6 m differ; no parity claim for this mode",
+    }
+    del tof32, kh32, h64, h32, both, same_ray, dts
+
     gather_info = None
     if args.gather and world > 1:
         from ray_tracing_ultrasound_b200 import sharding
@@ -318,6 +345,7 @@ def main():
             "gpu_launches": args.steps * 1,
             "roofline": roofline,
         }
+        out["fp32"] = fp32_info
         if gather_info:
             out["all_gather"] = gather_info
         if not args.no_cpu:

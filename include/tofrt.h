@@ -117,6 +117,12 @@ int tofrt_table_dev(tofrt_ctx *ctx, const double *d_radius, const double *d_offs
 int tofrt_table_host(tofrt_ctx *ctx, const double *radius, const double *offset, long long G,
                      double *tof, int *k_hit, const tofrt_ray_records *rec);
 
+/* FP32 mode of tofrt_table_dev (reported separately, no bit-parity claim): the same
+ * pipeline with the per-ray arithmetic in float; tof is float[G][E].  radius/offset stay
+ * double arrays so both modes share their inputs. */
+int tofrt_table_f32_dev(tofrt_ctx *ctx, const double *d_radius, const double *d_offset, long long G,
+                        float *d_tof, int *d_k_hit, void *stream);
+
 /* Roofline denominator, measured on the device the context lives on: FP64
  * instructions per second (thread-level) of a DFMA stream and of the un-fused
  * DMUL+DADD stream the search loop issues (SURVEY.md section 8 d). */

@@ -524,6 +524,231 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
     }
 }
 
+// =====================================================================================
+// FP32 mode (north_star: "FP32 mode reported separately with its measured max error").
+// Same pipeline, per-ray arithmetic in float with CUDA's float elementary functions; the
+// geometry-independent tables are the FP64 ones rounded to float.  No bit-parity is claimed for
+// this mode: tests/bench report max |dt| and the hit-decision differences against FP64.
+// =====================================================================================
+struct DevSetupF {
+    float c1, c2, fourAC, twoA, twod, K2, phi1, c1_over_c2;
+    float rtol, atol, tol_max, rx_min, rx_max, X, Z;
+    int K, E, E_sorted, has_nonfinite_rx, shape, log2n;
+    const float2 *lens, *seg;
+    const float *a_pq, *b_pq, *phi_pq, *z_f, *leg1, *x_rx, *xs;
+    const int *perm;
+};
+
+struct TableArgsF {
+    const double *radius, *offset;
+    long long G;
+    float *tof;
+    int *k_hit;
+    unsigned long long *counter;
+};
+
+__global__ void tofrt_to_float_kernel(int n, const double *src, float *dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+
+#define HALF_PI_F 1.57079632679489661923f
+
+__device__ __forceinline__ float line_diff_f(float2 s, float m, float b) { return s.y - (m * s.x + b); }
+__device__ __forceinline__ int sign_class_f(float v) { return v > 0 ? 2 : (v < 0 ? 0 : (v == 0 ? 1 : 3)); }
+__device__ __forceinline__ bool np_isclose_f(float a, float b, float rtol, float atol)
+{
+    return ((fabsf(a - b) <= atol + rtol * fabsf(b)) && isfinite(b)) || (a == b);
+}
+__device__ __forceinline__ float dist2d_f(float x1, float z1, float x2, float z2)
+{
+    return sqrtf((x1 - x2) * (x1 - x2) + (z1 - z2) * (z1 - z2));
+}
+__device__ __noinline__ int scan_exact_from_f(const float2 *lens, int N, float m, float b, int j0)
+{
+    int cprev = sign_class_f(line_diff_f(lens[j0], m, b));
+    for (int j = j0; j + 1 < N; ++j) {
+        int cnext = sign_class_f(line_diff_f(lens[j + 1], m, b));
+        if (class_change(cprev, cnext)) return j;
+        cprev = cnext;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF S, TableArgsF T)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = S.K, N = S.K, E = S.E;
+    float2 *s_lens = reinterpret_cast<float2 *>(smem_raw);
+    float2 *s_seg = s_lens + N;
+    float *s_xs = reinterpret_cast<float *>(s_seg + N);
+    float *s_tof = s_xs + S.E_sorted;                 // [kWarps][E]
+    int *s_perm = reinterpret_cast<int *>(s_tof + (size_t)kWarps * E);
+    int *s_khit = s_perm + S.E_sorted;                // [kWarps][E]
+    for (int i = threadIdx.x; i < N; i += kThreads) s_lens[i] = S.lens[i];
+    for (int i = threadIdx.x; i < N - 1; i += kThreads) s_seg[i] = S.seg[i];
+    for (int i = threadIdx.x; i < S.E_sorted; i += kThreads) { s_xs[i] = S.xs[i]; s_perm[i] = S.perm[i]; }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *w_tof = s_tof + (size_t)warp * E;
+    int *w_khit = s_khit + (size_t)warp * E;
+    const int nchunks = (K + 31) >> 5;
+    const unsigned FULL = 0xffffffffu;
+    for (;;) {
+        unsigned long long g64 = 0;
+        if (lane == 0) g64 = atomicAdd(T.counter, 1ull);
+        g64 = __shfl_sync(FULL, g64, 0);
+        if (g64 >= (unsigned long long)T.G) break;
+        const long long g = (long long)g64;
+        const float r_outer = (float)T.radius[g], pipe_offset = (float)T.offset[g];
+        const float rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset;
+        for (int e = lane; e < E; e += 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0f; }
+        __syncwarp();
+        for (int c = 0; c < nchunks; ++c) {
+            const int k = (c << 5) + lane;
+            const bool valid = k < K;
+            const int kk = valid ? k : K - 1;
+            const float a_pq = __ldg(S.a_pq + kk), b_pq = __ldg(S.b_pq + kk), phi_pq = __ldg(S.phi_pq + kk);
+            const float z_f = __ldg(S.z_f + kk);
+            float x_q, z_q;
+            {
+                float A2 = a_pq * a_pq + 1;
+                float B2 = 2 * (a_pq * b_pq - pipe_offset);
+                float C2 = offsq + b_pq * b_pq - rsq;
+                float sd = sqrtf(B2 * B2 - 4 * A2 * C2);
+                float den = 2 * A2;
+                float x_q1 = (-B2 + sd) / den, x_q2 = (-B2 - sd) / den;
+                float z_q1 = a_pq * x_q1 + b_pq, z_q2 = a_pq * x_q2 + b_pq;
+                bool up = z_q1 > z_q2;
+                x_q = up ? x_q1 : x_q2;
+                z_q = up ? z_q1 : z_q2;
+            }
+            float phi_l, m, b;
+            {
+                float slope = -x_q / sqrtf(rsq - x_q * x_q);
+                float phi_slope = atanf(slope);
+                float theta_1 = phi_pq - (phi_slope + HALF_PI_F);
+                phi_l = phi_slope - HALF_PI_F + (-theta_1);
+                m = tanf(phi_l);
+                b = z_q - m * x_q;
+            }
+            const bool fin = valid && fabsf(m) < 1e18f && fabsf(b) < 1e18f;
+            int idx = -1;
+            bool need_scan = fin, check_on_sample = false;
+            if (fin && S.shape != 0) {
+                const float sh = (float)S.shape;
+                const float tol = (fabsf(m) * S.X + fabsf(b) + S.Z) * 1.9073486328125e-06f /* 2^-19 */ + 1e-30f;
+                const float g0 = sh * line_diff_f(s_lens[0], m, b), gN = sh * line_diff_f(s_lens[N - 1], m, b);
+                int lo = 0, hi = 0;
+                bool bracket = false, none = false;
+                float edge = 0.f;
+                if (g0 > tol) {
+                    if (gN > tol) { none = true; edge = fminf(g0, gN) - tol; }
+                    else { bracket = true; hi = N - 1; }
+                } else if (g0 < -tol) {
+                    const float ms = sh * m;
+                    int l = 0, r = N - 1;
+                    while (l < r) { int mid = (l + r) >> 1; if (sh * s_seg[min(mid, N - 2)].x > ms) l = mid + 1; else r = mid; }
+                    const float gm = sh * line_diff_f(s_lens[l], m, b);
+                    if (gm < -tol) { none = true; edge = -gm - tol; }
+                    else if (gm > tol) { bracket = true; hi = l; }
+                }
+                if (bracket) {
+                    const bool pos0 = g0 > 0;
+                    while (hi - lo > 1) {
+                        int mid = (lo + hi) >> 1;
+                        float gmid = sh * line_diff_f(s_lens[mid], m, b);
+                        if (pos0 ? (gmid > tol) : (gmid < -tol)) lo = mid; else hi = mid;
+                    }
+                    idx = scan_exact_from_f(s_lens, N, m, b, lo);
+                    need_scan = false;
+                    check_on_sample = idx < 0;
+                } else if (none) {
+                    need_scan = false;
+                    check_on_sample = !(edge > 1e-8f);
+                }
+            }
+            if (valid && need_scan) { idx = scan_exact_from_f(s_lens, N, m, b, 0); check_on_sample = idx < 0; }
+            else if (valid && !fin) idx = scan_exact_from_f(s_lens, N, m, b, 0);
+            float ix = NAN, iz = NAN;
+            if (idx >= 0) {
+                float2 p1 = s_lens[idx], p2 = s_lens[idx + 1], sg = s_seg[idx];
+                if (np_isclose_f(p1.x, p2.x, 1e-5f, 1e-8f)) {
+                    float y_int = m * p1.x + b;
+                    if (y_int >= fminf(p1.y, p2.y) - 1e-9f && y_int <= fmaxf(p1.y, p2.y) + 1e-9f) { ix = p1.x; iz = y_int; }
+                } else if (np_isclose_f(m, sg.x, 1e-5f, 1e-8f)) {
+                    if (np_isclose_f(b, sg.y, 1e-5f, 1e-8f)) { ix = (p1.x + p2.x) / 2.0f; iz = m * ix + b; }
+                } else {
+                    float x_int = (sg.y - b) / (m - sg.x), y_int = m * x_int + b;
+                    if (x_int >= fminf(p1.x, p2.x) - 1e-9f && x_int <= fmaxf(p1.x, p2.x) + 1e-9f &&
+                        y_int >= fminf(p1.y, p2.y) - 1e-9f && y_int <= fmaxf(p1.y, p2.y) + 1e-9f) { ix = x_int; iz = y_int; }
+                }
+            } else if (valid && check_on_sample) {
+                for (int j = 0; j < N; ++j)
+                    if (fabsf(line_diff_f(s_lens[j], m, b)) <= 1e-8f) { ix = s_lens[j].x; iz = s_lens[j].y; break; }
+            }
+            float target_x;
+            {
+                float alpha_i = atan2f(ix, iz);
+                float sn, cs;
+                sincosf(alpha_i, &sn, &cs);
+                float B = S.twod * cs - S.K2;
+                float sd = sqrtf(B * B - S.fourAC);
+                float hh = (-B - sd) / S.twoA;
+                float dB = -S.twod * sn;
+                float dS = (1 / (2 * sd)) * (2 * B * dB);
+                float dh = S.phi1 * (dB + dS);
+                float dz = dh * cs - hh * sn, dx = dh * sn + hh * cs;
+                float phi_slope = atan2f(dz, dx);
+                float theta_1 = phi_l - (phi_slope + HALF_PI_F);
+                float theta_2 = asinf(S.c1_over_c2 * sinf(theta_1));
+                float phi_last = phi_slope - HALF_PI_F + theta_2;
+                float a_i = tanf(phi_last);
+                float b_i = iz - a_i * ix;
+                target_x = (z_f - b_i) / a_i;
+            }
+            bool cand = valid && target_x >= S.rx_min - S.tol_max && target_x <= S.rx_max + S.tol_max;
+            bool special = valid && S.has_nonfinite_rx && isinf(target_x);
+            if (__any_sync(FULL, cand || special)) {
+                int lo = 0, hi = 0;
+                bool mine = false;
+                if (cand) {
+                    float tl = target_x - S.tol_max, th = target_x + S.tol_max;
+                    int l = 0, r = S.E_sorted;
+                    while (l < r) { int mid = (l + r) >> 1; if (s_xs[mid] < tl) l = mid + 1; else r = mid; }
+                    lo = hi = l;
+                    while (hi < S.E_sorted && s_xs[hi] <= th) ++hi;
+                    for (int i = lo; i < hi; ++i)
+                        if (np_isclose_f(target_x, s_xs[i], S.rtol, S.atol)) { atomicMin(&w_khit[s_perm[i]], k); mine = true; }
+                }
+                if (special)
+                    for (int e = 0; e < E; ++e)
+                        if (target_x == S.x_rx[e]) { atomicMin(&w_khit[e], k); mine = true; }
+                __syncwarp();
+                if (mine) {
+                    float2 p = s_lens[kk];
+                    float tof = S.leg1[kk];
+                    tof += dist2d_f(p.x, p.y, x_q, z_q) / S.c2;
+                    tof += dist2d_f(x_q, z_q, ix, iz) / S.c2;
+                    tof += dist2d_f(ix, iz, target_x, z_f) / S.c1;
+                    for (int i = lo; i < hi; ++i) { int e = s_perm[i]; if (w_khit[e] == k) w_tof[e] = tof; }
+                    if (special) for (int e = 0; e < E; ++e) if (w_khit[e] == k) w_tof[e] = tof;
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        for (int e = lane; e < E; e += 32) {
+            int kh = w_khit[e];
+            T.tof[(size_t)g * E + e] = w_tof[e];
+            T.k_hit[(size_t)g * E + e] = kh == kNoHit ? -1 : kh;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- FP64 issue-rate micro-benchmark (the roofline denominator, measured on the box) ----
 // 8 independent dependency chains per thread; MODE 0: DFMA, MODE 1: DMUL+DADD (un-fused, as
 // the scan issues them).  Each loop iteration issues 16 FP64 instructions per thread.
@@ -577,6 +802,9 @@ struct tofrt_ctx {
     double *d_alpha = nullptr, *d_zf = nullptr, *d_a = nullptr, *d_b = nullptr, *d_phi = nullptr, *d_leg1 = nullptr;
     double2 *d_lens = nullptr, *d_seg = nullptr;
     int opt_guided = 1;
+    float *d_f32 = nullptr;   // FP32 copies of the tables (FP32 mode)
+    DevSetupF SF{};
+    size_t smem_f32 = 0;
     double *d_xrx = nullptr, *d_xs = nullptr;
     int *d_perm = nullptr, *d_bad = nullptr;
     unsigned long long *d_counter = nullptr;
@@ -589,9 +817,9 @@ struct tofrt_ctx {
     void free_all()
     {
         cudaFree(d_alpha); cudaFree(d_zf); cudaFree(d_a); cudaFree(d_b); cudaFree(d_phi); cudaFree(d_leg1);
-        cudaFree(d_lens); cudaFree(d_seg); cudaFree(d_xrx); cudaFree(d_xs); cudaFree(d_perm); cudaFree(d_bad);
+        cudaFree(d_lens); cudaFree(d_seg); cudaFree(d_f32); cudaFree(d_xrx); cudaFree(d_xs); cudaFree(d_perm); cudaFree(d_bad);
         d_alpha = d_zf = d_a = d_b = d_phi = d_leg1 = d_xrx = d_xs = nullptr;
-        d_lens = d_seg = nullptr; d_perm = d_bad = nullptr;
+        d_lens = d_seg = nullptr; d_perm = d_bad = nullptr; d_f32 = nullptr;
     }
 };
 
@@ -754,6 +982,40 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
         S.log2n = lg + 1;
     }
     S.guided = c->opt_guided;
+    // ---- FP32 mode: the same tables rounded to float ----
+    {
+        const int Es = std::max(1, S.E_sorted);
+        const size_t nf = (size_t)4 * K + (size_t)5 * K + E + Es;  // lens(2K) seg(2K) a,b,phi,zf,leg1 x_rx xs
+        CUDA_TRY(cudaMalloc(&c->d_f32, sizeof(float) * nf));
+        float *f = c->d_f32;
+        auto conv = [&](const double *src, int n) {
+            float *dst = f;
+            if (n > 0) tofrt_to_float_kernel<<<(n + 255) / 256, 256>>>(n, src, dst);
+            f += n;
+            return dst;
+        };
+        DevSetupF F{};
+        F.lens = (const float2 *)conv((const double *)c->d_lens, 2 * K);
+        F.seg = (const float2 *)conv((const double *)c->d_seg, 2 * K - 2); f += 2;
+        F.a_pq = conv(c->d_a, K); F.b_pq = conv(c->d_b, K); F.phi_pq = conv(c->d_phi, K);
+        F.z_f = conv(c->d_zf, K); F.leg1 = conv(c->d_leg1, K);
+        F.x_rx = conv(c->d_xrx, E); F.xs = conv(c->d_xs, S.E_sorted);
+        CUDA_TRY(cudaGetLastError());
+        F.perm = c->d_perm;
+        F.c1 = (float)S.c1; F.c2 = (float)S.c2; F.fourAC = (float)S.fourAC; F.twoA = (float)S.twoA;
+        F.twod = (float)S.twod; F.K2 = (float)S.K2; F.phi1 = (float)S.phi1; F.c1_over_c2 = (float)S.c1_over_c2;
+        F.rtol = (float)S.rtol; F.atol = (float)S.atol;
+        F.tol_max = (float)(S.tol_max * 1.001) + 1e-30f;
+        F.rx_min = (float)S.rx_min; F.rx_max = (float)S.rx_max; F.X = (float)S.X * 1.0001f; F.Z = (float)S.Z * 1.0001f;
+        F.K = K; F.E = E; F.E_sorted = S.E_sorted; F.has_nonfinite_rx = S.has_nonfinite_rx;
+        F.shape = S.shape; F.log2n = S.log2n;
+        c->SF = F;
+        c->smem_f32 = (size_t)2 * K * sizeof(float2) + (size_t)S.E_sorted * (sizeof(float) + sizeof(int)) +
+                      (size_t)kWarps * E * (sizeof(float) + sizeof(int)) + 16;
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)c->smem_f32));
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
 
     CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
@@ -824,6 +1086,25 @@ int tofrt_table_dev(tofrt_ctx *c, const double *d_radius, const double *d_offset
     long long warps_needed = G;
     int grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, (warps_needed + kWarps - 1) / kWarps);
     tofrt_table_kernel<<<grid, kThreads, c->smem, st>>>(c->S, T);
+    CUDA_TRY(cudaGetLastError());
+    return TOFRT_OK;
+}
+
+int tofrt_table_f32_dev(tofrt_ctx *c, const double *d_radius, const double *d_offset, long long G, float *d_tof,
+                        int *d_k_hit, void *stream)
+{
+    if (!c || G < 0) return fail(TOFRT_E_BADARG, "tofrt_table_f32_dev: bad argument");
+    if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_table_f32_dev: call tofrt_setup first");
+    if (G == 0) return TOFRT_OK;
+    if (!d_radius || !d_offset || !d_tof || !d_k_hit) return fail(TOFRT_E_BADARG, "tofrt_table_f32_dev: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TableArgsF T{};
+    T.radius = d_radius; T.offset = d_offset; T.G = G; T.tof = d_tof; T.k_hit = d_k_hit;
+    T.counter = c->d_counter;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
+    int grid = (int)std::min<long long>((long long)c->sm_count, (G + kWarps - 1) / kWarps);
+    tofrt_table_kernel_f32<<<grid, kThreads, c->smem_f32, st>>>(c->SF, T);
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
 }

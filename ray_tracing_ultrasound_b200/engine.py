@@ -152,6 +152,21 @@ class TofEngine:
                                               ctypes.c_void_p(stream)))
         return TofTable(tof, k_hit, out)
 
+    # ---- FP32 mode (reported separately: no bit-parity claim) ----------------------
+    def tof_table_f32_cuda(self, radii, offsets, out_tof=None, out_k_hit=None):
+        """Same table with the per-ray arithmetic in float32; radii/offsets are the float64 CUDA tensors."""
+        import torch
+        if not (radii.is_cuda and offsets.is_cuda and radii.dtype == torch.float64 and
+                offsets.dtype == torch.float64 and radii.is_contiguous() and offsets.is_contiguous()):
+            raise ValueError("radii/offsets must be contiguous float64 CUDA tensors")
+        G, dev = radii.numel(), radii.device
+        tof = out_tof if out_tof is not None else torch.empty((G, self.E), dtype=torch.float32, device=dev)
+        k_hit = out_k_hit if out_k_hit is not None else torch.empty((G, self.E), dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _capi.check(self._lib.tofrt_table_f32_dev(self._ctx, radii.data_ptr(), offsets.data_ptr(), G,
+                                                  tof.data_ptr(), k_hit.data_ptr(), ctypes.c_void_p(stream)))
+        return TofTable(tof, k_hit)
+
     # ---- main_rt.py:337-441 -----------------------------------------------------
     def shoot_rays(self, r_outer, pipe_offset, with_idx=False, with_legs=False):
         recs = ["pipe_x", "pipe_z", "lens2_x", "lens2_z", "target_x"]
