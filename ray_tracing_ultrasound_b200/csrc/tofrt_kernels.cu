@@ -301,41 +301,31 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                 const double tol = (fabs(m) * S.X + fabs(b) + S.Z) * 0x1p-48 + 1e-290;
                 const double g0 = sh * line_diff(s_lens[0], m, b);
                 const double gN = sh * line_diff(s_lens[N - 1], m, b);
-                // maximum of g: first chord whose slope (times shape) is <= shape*m
-                int jm;
-                {
-                    const double ms = sh * m;
-                    int l = 0, r = N - 1;  // answer in [0, N-1]
-                    for (int it = 0; it < S.log2n; ++it) {
-                        int mid = (l + r) >> 1;
-                        bool go = (l < r) && (sh * s_seg[min(mid, N - 2)].x > ms);
-                        l = go ? mid + 1 : l;
-                        r = (l < r && !go) ? mid : r;
-                    }
-                    jm = l;
-                }
-                int lo = 0, hi = 0;
+                const bool pos0 = g0 > tol, neg0 = g0 < -tol;
                 bool bracket = false, certain_none = false;
-                double edge = 0.0;  // |diff| closest to zero when there is certainly no change
-                if (fast) {
-                    if (g0 > tol) {
-                        if (gN > tol) { certain_none = true; edge = fmin(g0, gN) - tol; }
-                        else { bracket = true; lo = 0; hi = N - 1; }
-                    } else if (g0 < -tol) {
-                        const double gm = sh * line_diff(s_lens[jm], m, b);
-                        if (gm < -tol) { certain_none = true; edge = -gm - tol; }
-                        else if (gm > tol) { bracket = true; lo = 0; hi = jm; }
-                    }
-                }
-                // bisection: invariant g_lo beyond tol with the sign of g_0 (so is every sample before lo)
-                const bool pos0 = g0 > 0;
+                double edge = 0.0;  // lower bound of min|diff| when there is certainly no change
+                if (fast && pos0 && gN > tol) { certain_none = true; edge = fmin(g0, gN) - tol; }
+                else if (fast && (pos0 || neg0)) bracket = true;
+                // One bisection serves both cases.  lo advances to mid iff g_mid certainly has the
+                // sign of g_0 and, when g_0 < 0, mid is still before the maximum of g (chord slope
+                // on the rising side): then every sample up to mid certainly has that sign too.
+                const double sgn = pos0 ? sh : -sh;
+                const double ms_eff = pos0 ? -INFINITY : sh * m;
+                int lo = 0, hi = N - 1;
                 for (int it = 0; it < S.log2n; ++it) {
-                    int mid = (lo + hi) >> 1;
-                    double gmid = sh * line_diff(s_lens[mid], m, b);
-                    bool same = pos0 ? (gmid > tol) : (gmid < -tol);
-                    bool act = bracket && (hi - lo > 1);
-                    lo = (act && same) ? mid : lo;
-                    hi = (act && !same) ? mid : hi;
+                    const int mid = (lo + hi) >> 1;  // <= N-2 whenever hi - lo > 1
+                    const double dmid = line_diff(s_lens[mid], m, b);
+                    const bool cond = (sgn * dmid > tol) && (sh * s_seg[mid].x > ms_eff);
+                    const bool act = bracket && (hi - lo > 1);
+                    lo = (act && cond) ? mid : lo;
+                    hi = (act && !cond) ? mid : hi;
+                }
+                if (bracket && neg0) {
+                    // hi = lo + 1 failed the test (or is the untested last sample).  If g_hi is still
+                    // certainly negative, hi is at/after the maximum while lo is before it: g_hi IS
+                    // the maximum of g, so no diff is >= 0.
+                    const double ghi = sh * line_diff(s_lens[hi], m, b);
+                    if (ghi < -tol) { bracket = false; certain_none = true; edge = -ghi - tol; }
                 }
                 if (bracket) {
                     // exact classes from lo on (normally one step)
@@ -346,9 +336,8 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                         if (class_change(cprev, cnext)) break;
                         cprev = cnext;
                     }
-                    if (j + 1 < N) { idx = j; need_scan = false; }
-                    else { need_scan = false; }  // no change after lo either: certainly none before it
-                    // (possible only when the far end is within tol of zero; the on-sample test below decides)
+                    if (j + 1 < N) idx = j;
+                    need_scan = false;  // no change after lo either => none at all (on-sample test decides)
                 } else if (certain_none) {
                     need_scan = false;
                     skip_on_sample = edge > 1e-8;  // every |diff| > 1e-8: main_rt.py:86-96 returns None
@@ -429,16 +418,25 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
             else if (on_sample >= 0) { double2 s = s_lens[on_sample]; ix = s.x; iz = s.y; }
 
             // ---- main_rt.py:396-405 refraction back into the lens, landing point ----
-            double target_x;
-            {
+            // NaN in -> NaN out, so whole 32-ray groups that missed the lens, or are totally
+            // reflected (|sin| > 1 in main_rt.py:277), skip the rest of the arithmetic.
+            double target_x = NAN;
+            if (__any_sync(FULL, valid && ix == ix)) {
                 double alpha_i = tofrt_atan2(ix, iz);
                 double sn, cs, h, dz, dx;
                 tofrt_sincos(alpha_i, &sn, &cs);
                 lens_point(S, sn, cs, &h, &dz, &dx);
-                double phi_last = refract(phi_l, dz, dx, S.c1_over_c2);
-                double a_i = tofrt_tan(phi_last);
-                double b_i = iz - a_i * ix;
-                target_x = (z_f - b_i) / a_i;
+                // refraction(phi_l, (dz, dx), c2, c1), main_rt.py:272-278
+                double phi_slope = tofrt_atan2(dz, dx);
+                double theta_1 = phi_l - (phi_slope + HALF_PI);
+                double s_arg = S.c1_over_c2 * tofrt_sin(theta_1);
+                if (__any_sync(FULL, valid && fabs(s_arg) <= 1.0)) {
+                    double theta_2 = tofrt_asin(s_arg);
+                    double phi_last = phi_slope - HALF_PI + theta_2;
+                    double a_i = tofrt_tan(phi_last);
+                    double b_i = iz - a_i * ix;
+                    target_x = (z_f - b_i) / a_i;
+                }
             }
 
             // ---- optional per-ray records ----

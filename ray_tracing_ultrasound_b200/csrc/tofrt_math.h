@@ -34,9 +34,15 @@
 
 #if defined(__CUDACC__)
 #define TOFRT_HD __device__ __forceinline__
+#ifdef TOFRT_MATH_NOINLINE /* tuning knob: one shared copy of the two big functions */
+#define TOFRT_HD_BIG __device__ __noinline__
+#else
+#define TOFRT_HD_BIG __device__ __forceinline__
+#endif
 #define TOFRT_TABLE static __constant__ double
 #else
 #define TOFRT_HD static inline
+#define TOFRT_HD_BIG static inline
 #define TOFRT_TABLE static const double
 #endif
 
@@ -102,7 +108,7 @@ TOFRT_HD void tofrt_sincos_kernel(double x, double y, double *sn, double *cs)
  * Cody-Waite reduction whose first step is exact (fma) and whose remainder is
  * kept as a double-double, so the result keeps full relative accuracy near
  * multiples of pi/2.  Returns sin(r + rl), cos(r + rl) and n mod 4. */
-TOFRT_HD int tofrt_sincos_reduced(double x, double *s, double *c)
+TOFRT_HD_BIG int tofrt_sincos_reduced(double x, double *s, double *c)
 {
     double t = fma(x, TK(TWO_OVER_PI), TK(MAGIC));
     double n = t - TK(MAGIC);
@@ -158,7 +164,7 @@ TOFRT_HD double tofrt_tan(double x)
  * atan(a/b) = atan(u) for u = a/b when a < 7/16 b, else pi/4 + atan(u) with
  * u = (a-b)/(a+b) in (-0.392, 0]; then the octant is undone with hi/lo splits
  * of pi/2 and pi. */
-TOFRT_HD double tofrt_atan2(double y, double x)
+TOFRT_HD_BIG double tofrt_atan2(double y, double x)
 {
     double ax = fabs(x), ay = fabs(y);
     int swap = ay > ax;

@@ -5,9 +5,7 @@
 import os, subprocess, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = {"t512_b1": ("TOFRT_THREADS=512", "TOFRT_MIN_BLOCKS=1"), "t512_b2": ("TOFRT_THREADS=512", "TOFRT_MIN_BLOCKS=2"),
-            "t256_b3": ("TOFRT_THREADS=256", "TOFRT_MIN_BLOCKS=3"), "t256_b4": ("TOFRT_THREADS=256", "TOFRT_MIN_BLOCKS=4"),
-            "t1024_b1": ("TOFRT_THREADS=1024", "TOFRT_MIN_BLOCKS=1"), "t384_b2": ("TOFRT_THREADS=384", "TOFRT_MIN_BLOCKS=2")}
+VARIANTS = {"base": (), "noinline": ("TOFRT_MATH_NOINLINE",)}
 VDIR = os.path.join(ROOT, "tools", "_variants")
 
 if sys.argv[1] == "build":
