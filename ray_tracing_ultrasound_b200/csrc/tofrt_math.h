@@ -17,10 +17,11 @@
  * polynomial coefficients live in constant memory on the device so that each
  * Horner step is a single DFMA with a c[bank][offset] operand.
  *
- * Accuracy (tests/test_math.py, against mpmath): sin, cos < 1 ulp; tan, atan,
+ * Accuracy (tests/test_math.py, against mpmath): sin, cos < 1.5 ulp; tan, atan,
  * atan2 < 2.5 ulp; asin < 3 ulp.  Domain of the trigonometric reduction:
  * |x| < 2^30 (angles in this engine never leave [-4 pi, 4 pi]); larger finite
- * arguments return NaN instead of a value with no correct digits.
+ * arguments return NaN instead of a value with no correct digits.  sin/tan of
+ * -0.0 return +0.0 (the sign of a zero is not preserved).
  *
  * Compile without floating-point contraction (nvcc -fmad=false,
  * gcc -ffp-contract=off): every fused operation below is an explicit fma().
@@ -89,37 +90,30 @@ TOFRT_HD uint32_t tofrt_lo32(double v)
 #endif
 }
 
-/* sin and cos of (x + y) for |x| <= pi/4 (+ a few ulp), y the tail of x */
-TOFRT_HD void tofrt_sincos_kernel(double x, double y, double *sn, double *cs)
+/* sin and cos for |x| <= pi/4 (+ a few ulp) */
+TOFRT_HD void tofrt_sincos_kernel(double x, double *sn, double *cs)
 {
     double z = x * x;
     /* sin */
-    double rs = fma(z, fma(z, fma(z, fma(z, TK(S6), TK(S5)), TK(S4)), TK(S3)), TK(S2));
-    double v = z * x;
-    *sn = x - ((z * (0.5 * y - v * rs) - y) - v * TK(S1));
+    double rs = fma(z, fma(z, fma(z, fma(z, fma(z, TK(S6), TK(S5)), TK(S4)), TK(S3)), TK(S2)), TK(S1));
+    *sn = fma(z * x, rs, x);
     /* cos */
     double rc = z * fma(z, fma(z, fma(z, fma(z, fma(z, TK(C6), TK(C5)), TK(C4)), TK(C3)), TK(C2)), TK(C1));
     double hz = 0.5 * z;
     double w = 1.0 - hz;
-    *cs = w + (((1.0 - w) - hz) + (z * rc - x * y));
+    *cs = w + (((1.0 - w) - hz) + z * rc);
 }
 
-/* Quadrant-reduced sine and cosine: x = n*(pi/2) + (r + rl) by a three-term
- * Cody-Waite reduction whose first step is exact (fma) and whose remainder is
- * kept as a double-double, so the result keeps full relative accuracy near
- * multiples of pi/2.  Returns sin(r + rl), cos(r + rl) and n mod 4. */
+/* Quadrant-reduced sine and cosine: x = n*(pi/2) + r by a two-term Cody-Waite reduction whose
+ * first step is exact (fma) and whose second step rounds once, relative to r itself, so the
+ * result keeps its relative accuracy near multiples of pi/2 (the neglected third term is
+ * n * 1.5e-33).  Returns sin(r), cos(r) and n mod 4. */
 TOFRT_HD_BIG int tofrt_sincos_reduced(double x, double *s, double *c)
 {
     double t = fma(x, TK(TWO_OVER_PI), TK(MAGIC));
     double n = t - TK(MAGIC);
-    double r1 = fma(-n, TK(PIO2_HI), x); /* exact */
-    double ph = n * TK(PIO2_MID);
-    double pl = fma(n, TK(PIO2_MID), -ph); /* ph + pl = n * MID exactly */
-    double r = r1 - ph;                    /* two-sum of r1 + (-ph) */
-    double bb = r - r1;
-    double e = (r1 - (r - bb)) + (-ph - bb);
-    double rl = fma(-n, TK(PIO2_LO), e - pl);
-    tofrt_sincos_kernel(r, rl, s, c);
+    double r = fma(-n, TK(PIO2_MID), fma(-n, TK(PIO2_HI), x));
+    tofrt_sincos_kernel(r, s, c);
     return (int)(tofrt_lo32(t) & 3u); /* the magic constant leaves n in the low mantissa bits */
 }
 
