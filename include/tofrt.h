@@ -79,6 +79,14 @@ int tofrt_setup(tofrt_ctx *ctx, const tofrt_params *params, const double *alpha,
                 int K, double x_shooter, double z_shooter, const double *x_rx, int E, double rtol,
                 double atol);
 
+/* Full-matrix capture: the same setup for S shooters at once (the reference
+ * shoots only element 32, main_rt.py:481-482; any element can shoot).  After this call the
+ * table functions trace every shooter for every geometry: outputs are tof[s][g][e],
+ * k_hit[s][g][e] and records [s][g][K] -- S blocks in the single-shooter layout. */
+int tofrt_setup_shooters(tofrt_ctx *ctx, const tofrt_params *params, const double *alpha,
+                         const double *z_f, int K, const double *x_shooters, const double *z_shooters,
+                         int n_shooters, const double *x_rx, int E, double rtol, double atol);
+
 /* Options.  TOFRT_OPT_SEARCH selects how the return-path entry index of
  * find_line_curve_intersection (main_rt.py:78-99) is found:
  *   TOFRT_SEARCH_SCAN    the reference's literal first-sign-change scan over all

@@ -30,7 +30,7 @@ class RayRecords(ctypes.Structure):
 
 
 EXPORTS = ["tofrt_version", "tofrt_last_error", "tofrt_device_count", "tofrt_create", "tofrt_destroy",
-           "tofrt_setup", "tofrt_set_option", "tofrt_get_info", "tofrt_last_stats", "tofrt_lens_host", "tofrt_table_dev", "tofrt_table_f32_dev", "tofrt_table_host", "tofrt_kernel_info", "tofrt_measure_fp64_peak"]
+           "tofrt_setup", "tofrt_setup_shooters", "tofrt_set_option", "tofrt_get_info", "tofrt_last_stats", "tofrt_lens_host", "tofrt_table_dev", "tofrt_table_f32_dev", "tofrt_table_host", "tofrt_kernel_info", "tofrt_measure_fp64_peak"]
 
 _lib = None
 
@@ -54,6 +54,9 @@ def load():
     lib.tofrt_setup.argtypes = [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
                                 ctypes.c_double, ctypes.c_double]
+    lib.tofrt_setup_shooters.argtypes = [ctypes.c_void_p, ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_double, ctypes.c_double]
     lib.tofrt_set_option.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     lib.tofrt_get_info.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.tofrt_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]

@@ -59,7 +59,8 @@ struct DevSetup {
     double c1, c2, d;
     double A, fourAC, twoA, twod, K2, phi1;  // lens surface (main_rt.py:181-212)
     double c2_over_c1, c1_over_c2;           // v2 / v1 of the two refractions
-    double x_sh, z_sh;                       // shooter
+    int n_shooters;                          // S: shots per geometry (full-matrix capture when S = E)
+    const double *x_sh, *z_sh;               // [S] shooter positions
     double rtol, atol, tol_max;              // np.isclose tolerances, and an upper bound of atol+rtol|x_e|
     double rx_min, rx_max;                   // finite receiver range
     int K, Npad, E, E_sorted, has_nonfinite_rx, tables_ok;
@@ -82,6 +83,7 @@ struct TableArgs {
     double *tof;
     int *k_hit;
     tofrt_ray_records rec;
+    int s_begin, s_count;  // shooters [s_begin, s_begin + s_count) of the setup; outputs are [s_count][G][...]
     unsigned long long *counter;
     unsigned long long *stats;  // [4]: rays traced, rays that needed the O(N) scan, warp-chunks that ran it, on-sample passes
 };
@@ -152,13 +154,17 @@ __global__ void tofrt_prepare_kernel(DevSetup S, const double *alpha, double2 *l
     lens[k] = make_double2(x_p, z_p);
     if (k >= S.K) return;
     if (!(fabs(x_p) < 1e150 && fabs(z_p) < 1e150)) atomicOr(bad, 1);
-    double phi_ap = tofrt_atan2(S.z_sh - z_p, S.x_sh - x_p);
-    double phi = refract(phi_ap, dz, dx, S.c2_over_c1);
-    double a = tofrt_tan(phi);
-    a_pq[k] = a;
-    b_pq[k] = z_p - a * x_p;
-    phi_pq[k] = phi;
-    leg1[k] = dist2d(S.x_sh, S.z_sh, x_p, z_p) / S.c1;
+    for (int s = 0; s < S.n_shooters; ++s) {  // main_rt.py:341-349 for every shooter
+        const double x_sh = S.x_sh[s], z_sh = S.z_sh[s];
+        double phi_ap = tofrt_atan2(z_sh - z_p, x_sh - x_p);
+        double phi = refract(phi_ap, dz, dx, S.c2_over_c1);
+        double a = tofrt_tan(phi);
+        size_t o = (size_t)s * S.K + k;
+        a_pq[o] = a;
+        b_pq[o] = z_p - a * x_p;
+        phi_pq[o] = phi;
+        leg1[o] = dist2d(x_sh, z_sh, x_p, z_p) / S.c1;
+    }
 }
 
 // chords of the sampled lens, main_rt.py:127-128 (geometry-independent, so computed once)
@@ -241,8 +247,10 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
         unsigned long long g64 = 0;
         if (lane == 0) g64 = atomicAdd(T.counter, 1ull);
         g64 = __shfl_sync(FULL, g64, 0);
-        if (g64 >= (unsigned long long)T.G) break;
-        const long long g = (long long)g64;
+        if (g64 >= (unsigned long long)T.G * (unsigned long long)T.s_count) break;
+        const long long w = (long long)g64;               // work item = (shooter, geometry)
+        const long long g = w % T.G;
+        const size_t sk = (size_t)(T.s_begin + w / T.G) * K;  // offset of the shooter's per-ray tables
         const double r_outer = T.radius[g], pipe_offset = T.offset[g];
         const double rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset;
         for (int e = lane; e < E; e += 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0; }
@@ -253,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
             const bool valid = k < K;
             const int kk = valid ? k : K - 1;
             // per-ray constants of the shot: one coalesced, L1-resident load per 32 rays
-            const double a_pq = __ldg(S.a_pq + kk), b_pq = __ldg(S.b_pq + kk), phi_pq = __ldg(S.phi_pq + kk);
+            const double a_pq = __ldg(S.a_pq + sk + kk), b_pq = __ldg(S.b_pq + sk + kk), phi_pq = __ldg(S.phi_pq + sk + kk);
             const double z_f = __ldg(S.z_f + kk);
 
             // ---- main_rt.py:351-364 pipe intersection, upper root ----
@@ -441,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
 
             // ---- optional per-ray records ----
             if (valid) {
-                size_t o = (size_t)g * K + k;
+                size_t o = (size_t)w * K + k;
                 if (T.rec.pipe_x) T.rec.pipe_x[o] = x_q;
                 if (T.rec.pipe_z) T.rec.pipe_z[o] = z_q;
                 if (T.rec.lens2_x) T.rec.lens2_x[o] = ix;
@@ -478,12 +486,12 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                 if (mine || (want_legs && valid)) {
                     // main_rt.py:497-500 / main_compare.py:514-517
                     double2 p = s_lens[kk];
-                    double t1 = S.leg1[kk];
+                    double t1 = S.leg1[sk + kk];
                     double t2 = dist2d(p.x, p.y, x_q, z_q) / S.c2;
                     double t3 = dist2d(x_q, z_q, ix, iz) / S.c2;
                     double t4 = dist2d(ix, iz, target_x, z_f) / S.c1;
                     if (want_legs) {
-                        size_t o = (size_t)g * 4 * K + k;
+                        size_t o = (size_t)w * 4 * K + k;
                         T.rec.legs[o] = t1; T.rec.legs[o + K] = t2;
                         T.rec.legs[o + 2 * (size_t)K] = t3; T.rec.legs[o + 3 * (size_t)K] = t4;
                     }
@@ -508,8 +516,8 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
         __syncwarp();
         for (int e = lane; e < E; e += 32) {
             int kh = w_khit[e];
-            T.tof[(size_t)g * E + e] = w_tof[e];
-            T.k_hit[(size_t)g * E + e] = kh == kNoHit ? -1 : kh;
+            T.tof[(size_t)w * E + e] = w_tof[e];
+            T.k_hit[(size_t)w * E + e] = kh == kNoHit ? -1 : kh;
         }
         __syncwarp();
     }
@@ -531,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
 struct DevSetupF {
     float c1, c2, fourAC, twoA, twod, K2, phi1, c1_over_c2;
     float rtol, atol, tol_max, rx_min, rx_max, X, Z;
-    int K, E, E_sorted, has_nonfinite_rx, shape, log2n;
+    int K, E, E_sorted, has_nonfinite_rx, shape, log2n, n_shooters;
     const float2 *lens, *seg;
     const float *a_pq, *b_pq, *phi_pq, *z_f, *leg1, *x_rx, *xs;
     const int *perm;
@@ -542,6 +550,7 @@ struct TableArgsF {
     long long G;
     float *tof;
     int *k_hit;
+    int s_begin, s_count;
     unsigned long long *counter;
 };
 
@@ -598,8 +607,10 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
         unsigned long long g64 = 0;
         if (lane == 0) g64 = atomicAdd(T.counter, 1ull);
         g64 = __shfl_sync(FULL, g64, 0);
-        if (g64 >= (unsigned long long)T.G) break;
-        const long long g = (long long)g64;
+        if (g64 >= (unsigned long long)T.G * (unsigned long long)T.s_count) break;
+        const long long w = (long long)g64;
+        const long long g = w % T.G;
+        const size_t sk = (size_t)(T.s_begin + w / T.G) * K;
         const float r_outer = (float)T.radius[g], pipe_offset = (float)T.offset[g];
         const float rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset;
         for (int e = lane; e < E; e += 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0f; }
@@ -608,7 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
             const int k = (c << 5) + lane;
             const bool valid = k < K;
             const int kk = valid ? k : K - 1;
-            const float a_pq = __ldg(S.a_pq + kk), b_pq = __ldg(S.b_pq + kk), phi_pq = __ldg(S.phi_pq + kk);
+            const float a_pq = __ldg(S.a_pq + sk + kk), b_pq = __ldg(S.b_pq + sk + kk), phi_pq = __ldg(S.phi_pq + sk + kk);
             const float z_f = __ldg(S.z_f + kk);
             float x_q, z_q;
             {
@@ -727,7 +738,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
                 __syncwarp();
                 if (mine) {
                     float2 p = s_lens[kk];
-                    float tof = S.leg1[kk];
+                    float tof = S.leg1[sk + kk];
                     tof += dist2d_f(p.x, p.y, x_q, z_q) / S.c2;
                     tof += dist2d_f(x_q, z_q, ix, iz) / S.c2;
                     tof += dist2d_f(ix, iz, target_x, z_f) / S.c1;
@@ -740,8 +751,8 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
         __syncwarp();
         for (int e = lane; e < E; e += 32) {
             int kh = w_khit[e];
-            T.tof[(size_t)g * E + e] = w_tof[e];
-            T.k_hit[(size_t)g * E + e] = kh == kNoHit ? -1 : kh;
+            T.tof[(size_t)w * E + e] = w_tof[e];
+            T.k_hit[(size_t)w * E + e] = kh == kNoHit ? -1 : kh;
         }
         __syncwarp();
     }
@@ -803,7 +814,8 @@ struct tofrt_ctx {
     float *d_f32 = nullptr;   // FP32 copies of the tables (FP32 mode)
     DevSetupF SF{};
     size_t smem_f32 = 0;
-    double *d_xrx = nullptr, *d_xs = nullptr;
+    double *d_xrx = nullptr, *d_xs = nullptr, *d_sh = nullptr;
+    int n_shooters = 1;
     int *d_perm = nullptr, *d_bad = nullptr;
     unsigned long long *d_counter = nullptr;
     // host-buffer pipeline (tofrt_table_host)
@@ -815,9 +827,9 @@ struct tofrt_ctx {
     void free_all()
     {
         cudaFree(d_alpha); cudaFree(d_zf); cudaFree(d_a); cudaFree(d_b); cudaFree(d_phi); cudaFree(d_leg1);
-        cudaFree(d_lens); cudaFree(d_seg); cudaFree(d_f32); cudaFree(d_xrx); cudaFree(d_xs); cudaFree(d_perm); cudaFree(d_bad);
+        cudaFree(d_lens); cudaFree(d_seg); cudaFree(d_f32); cudaFree(d_sh); cudaFree(d_xrx); cudaFree(d_xs); cudaFree(d_perm); cudaFree(d_bad);
         d_alpha = d_zf = d_a = d_b = d_phi = d_leg1 = d_xrx = d_xs = nullptr;
-        d_lens = d_seg = nullptr; d_perm = d_bad = nullptr; d_f32 = nullptr;
+        d_lens = d_seg = nullptr; d_perm = d_bad = nullptr; d_f32 = nullptr; d_sh = nullptr;
     }
 };
 
@@ -871,9 +883,19 @@ int tofrt_destroy(tofrt_ctx *c)
 int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const double *z_f, int K,
                 double x_shooter, double z_shooter, const double *x_rx, int E, double rtol, double atol)
 {
-    if (!c || !p || !alpha || !z_f || !x_rx) return fail(TOFRT_E_BADARG, "tofrt_setup: NULL argument");
+    return tofrt_setup_shooters(c, p, alpha, z_f, K, &x_shooter, &z_shooter, 1, x_rx, E, rtol, atol);
+}
+
+int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const double *z_f, int K,
+                         const double *x_shooters, const double *z_shooters, int n_shooters, const double *x_rx,
+                         int E, double rtol, double atol)
+{
+    if (!c || !p || !alpha || !z_f || !x_rx || !x_shooters || !z_shooters)
+        return fail(TOFRT_E_BADARG, "tofrt_setup: NULL argument");
     if (K < 2) return fail(TOFRT_E_TOOFEW, "Curve needs at least two points.");
     if (E < 1) return fail(TOFRT_E_BADARG, "tofrt_setup: need at least one receiver");
+    if (n_shooters < 1) return fail(TOFRT_E_BADARG, "tofrt_setup: need at least one shooter");
+    const int NS = n_shooters;
     CUDA_TRY(cudaSetDevice(c->device));
     c->ready = false;
     c->free_all();
@@ -893,7 +915,7 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
     S.phi1 = -1 / (2 * S.A);
     S.c2_over_c1 = p->c2 / p->c1;
     S.c1_over_c2 = p->c1 / p->c2;
-    S.x_sh = x_shooter; S.z_sh = z_shooter;
+    S.n_shooters = NS;
     S.rtol = rtol; S.atol = atol;
     S.K = K; S.E = E;
     S.Npad = 1 + ((K - 1 + kChunk - 1) / kChunk) * kChunk;
@@ -925,13 +947,16 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
 
     CUDA_TRY(cudaMalloc(&c->d_alpha, sizeof(double) * K));
     CUDA_TRY(cudaMalloc(&c->d_zf, sizeof(double) * K));
-    CUDA_TRY(cudaMalloc(&c->d_a, sizeof(double) * K));
-    CUDA_TRY(cudaMalloc(&c->d_b, sizeof(double) * K));
-    CUDA_TRY(cudaMalloc(&c->d_phi, sizeof(double) * K));
-    CUDA_TRY(cudaMalloc(&c->d_leg1, sizeof(double) * K));
+    CUDA_TRY(cudaMalloc(&c->d_a, sizeof(double) * K * NS));
+    CUDA_TRY(cudaMalloc(&c->d_b, sizeof(double) * K * NS));
+    CUDA_TRY(cudaMalloc(&c->d_phi, sizeof(double) * K * NS));
+    CUDA_TRY(cudaMalloc(&c->d_leg1, sizeof(double) * K * NS));
     CUDA_TRY(cudaMalloc(&c->d_lens, sizeof(double2) * S.Npad));
     CUDA_TRY(cudaMalloc(&c->d_seg, sizeof(double2) * K));
     CUDA_TRY(cudaMalloc(&c->d_xrx, sizeof(double) * E));
+    CUDA_TRY(cudaMalloc(&c->d_sh, sizeof(double) * 2 * NS));
+    CUDA_TRY(cudaMemcpy(c->d_sh, x_shooters, sizeof(double) * NS, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->d_sh + NS, z_shooters, sizeof(double) * NS, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&c->d_xs, sizeof(double) * std::max(1, S.E_sorted)));
     CUDA_TRY(cudaMalloc(&c->d_perm, sizeof(int) * std::max(1, S.E_sorted)));
     CUDA_TRY(cudaMemcpy(c->d_alpha, alpha, sizeof(double) * K, cudaMemcpyHostToDevice));
@@ -943,6 +968,7 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
     }
     CUDA_TRY(cudaMemset(c->d_bad, 0, sizeof(int)));
     S.lens = c->d_lens; S.seg = c->d_seg; S.a_pq = c->d_a; S.b_pq = c->d_b; S.phi_pq = c->d_phi; S.z_f = c->d_zf;
+    S.x_sh = c->d_sh; S.z_sh = c->d_sh + NS;
     S.leg1 = c->d_leg1; S.x_rx = c->d_xrx; S.xs = c->d_xs; S.perm = c->d_perm;
 
     tofrt_prepare_kernel<<<(S.Npad + 127) / 128, 128>>>(S, c->d_alpha, c->d_lens, c->d_a, c->d_b, c->d_phi,
@@ -983,7 +1009,7 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
     // ---- FP32 mode: the same tables rounded to float ----
     {
         const int Es = std::max(1, S.E_sorted);
-        const size_t nf = (size_t)4 * K + (size_t)5 * K + E + Es;  // lens(2K) seg(2K) a,b,phi,zf,leg1 x_rx xs
+        const size_t nf = (size_t)4 * K + (size_t)4 * K * NS + K + E + Es;  // lens(2K) seg(2K) [a,b,phi,leg1](S*K) zf x_rx xs
         CUDA_TRY(cudaMalloc(&c->d_f32, sizeof(float) * nf));
         float *f = c->d_f32;
         auto conv = [&](const double *src, int n) {
@@ -995,8 +1021,8 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
         DevSetupF F{};
         F.lens = (const float2 *)conv((const double *)c->d_lens, 2 * K);
         F.seg = (const float2 *)conv((const double *)c->d_seg, 2 * K - 2); f += 2;
-        F.a_pq = conv(c->d_a, K); F.b_pq = conv(c->d_b, K); F.phi_pq = conv(c->d_phi, K);
-        F.z_f = conv(c->d_zf, K); F.leg1 = conv(c->d_leg1, K);
+        F.a_pq = conv(c->d_a, K * NS); F.b_pq = conv(c->d_b, K * NS); F.phi_pq = conv(c->d_phi, K * NS);
+        F.z_f = conv(c->d_zf, K); F.leg1 = conv(c->d_leg1, K * NS);
         F.x_rx = conv(c->d_xrx, E); F.xs = conv(c->d_xs, S.E_sorted);
         CUDA_TRY(cudaGetLastError());
         F.perm = c->d_perm;
@@ -1006,7 +1032,7 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
         F.tol_max = (float)(S.tol_max * 1.001) + 1e-30f;
         F.rx_min = (float)S.rx_min; F.rx_max = (float)S.rx_max; F.X = (float)S.X * 1.0001f; F.Z = (float)S.Z * 1.0001f;
         F.K = K; F.E = E; F.E_sorted = S.E_sorted; F.has_nonfinite_rx = S.has_nonfinite_rx;
-        F.shape = S.shape; F.log2n = S.log2n;
+        F.shape = S.shape; F.log2n = S.log2n; F.n_shooters = NS;
         c->SF = F;
         c->smem_f32 = (size_t)2 * K * sizeof(float2) + (size_t)S.E_sorted * (sizeof(float) + sizeof(int)) +
                       (size_t)kWarps * E * (sizeof(float) + sizeof(int)) + 16;
@@ -1019,7 +1045,7 @@ int tofrt_setup(tofrt_ctx *c, const tofrt_params *p, const double *alpha, const 
     int occ = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel, kThreads, smem));
     c->ctas_per_sm = std::max(1, occ);
-    c->S = S; c->K = K; c->E = E; c->smem = smem;
+    c->S = S; c->K = K; c->E = E; c->smem = smem; c->n_shooters = NS;
     c->ready = true;
     return TOFRT_OK;
 }
@@ -1066,8 +1092,8 @@ int tofrt_lens_host(tofrt_ctx *c, double *lens_x, double *lens_z)
     return TOFRT_OK;
 }
 
-int tofrt_table_dev(tofrt_ctx *c, const double *d_radius, const double *d_offset, long long G, double *d_tof,
-                    int *d_k_hit, const tofrt_ray_records *d_rec, void *stream)
+static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_offset, long long G, double *d_tof,
+                          int *d_k_hit, const tofrt_ray_records *d_rec, void *stream, int s_begin, int s_count)
 {
     if (!c || G < 0) return fail(TOFRT_E_BADARG, "tofrt_table_dev: bad argument");
     if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_table_dev: call tofrt_setup first");
@@ -1078,14 +1104,21 @@ int tofrt_table_dev(tofrt_ctx *c, const double *d_radius, const double *d_offset
     TableArgs T{};
     T.radius = d_radius; T.offset = d_offset; T.G = G; T.tof = d_tof; T.k_hit = d_k_hit;
     if (d_rec) T.rec = *d_rec;
+    T.s_begin = s_begin; T.s_count = s_count;
     T.counter = c->d_counter;
     T.stats = c->d_counter + 1;
     CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
-    long long warps_needed = G;
+    long long warps_needed = G * s_count;
     int grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, (warps_needed + kWarps - 1) / kWarps);
     tofrt_table_kernel<<<grid, kThreads, c->smem, st>>>(c->S, T);
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
+}
+
+int tofrt_table_dev(tofrt_ctx *c, const double *d_radius, const double *d_offset, long long G, double *d_tof,
+                    int *d_k_hit, const tofrt_ray_records *d_rec, void *stream)
+{
+    return table_dev_impl(c, d_radius, d_offset, G, d_tof, d_k_hit, d_rec, stream, 0, c ? c->n_shooters : 1);
 }
 
 int tofrt_table_f32_dev(tofrt_ctx *c, const double *d_radius, const double *d_offset, long long G, float *d_tof,
@@ -1099,9 +1132,10 @@ int tofrt_table_f32_dev(tofrt_ctx *c, const double *d_radius, const double *d_of
     cudaStream_t st = (cudaStream_t)stream;
     TableArgsF T{};
     T.radius = d_radius; T.offset = d_offset; T.G = G; T.tof = d_tof; T.k_hit = d_k_hit;
+    T.s_begin = 0; T.s_count = c->n_shooters;
     T.counter = c->d_counter;
     CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
-    int grid = (int)std::min<long long>((long long)c->sm_count, (G + kWarps - 1) / kWarps);
+    int grid = (int)std::min<long long>((long long)c->sm_count, (G * c->n_shooters + kWarps - 1) / kWarps);
     tofrt_table_kernel_f32<<<grid, kThreads, c->smem_f32, st>>>(c->SF, T);
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
@@ -1160,10 +1194,14 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
     CUDA_TRY(cudaMemcpyAsync(c->d_in + g, offset, sizeof(double) * g, cudaMemcpyHostToDevice, c->s_compute));
 
     int rc = TOFRT_OK;
-    size_t done = 0;
-    for (int i = 0; done < g && rc == TOFRT_OK; ++i, done += chunk) {
-        const int slot = i & 1;
+    const size_t n_chunks = (g + chunk - 1) / chunk;
+    // one (shooter, chunk) launch at a time; host layout is [S][G][...] so each lands contiguously
+    for (size_t i = 0; i < n_chunks * (size_t)c->n_shooters && rc == TOFRT_OK; ++i) {
+        const int slot = (int)(i & 1);
+        const int sh = (int)(i / n_chunks);
+        const size_t done = (i % n_chunks) * chunk;
         const size_t n = std::min(chunk, g - done);
+        const size_t hbase = (size_t)sh * g + done;  // first host row of this launch
         // carve the slot
         char *base = (char *)c->ws[slot];
         auto take = [&](size_t bytes) { char *q = base; base += (bytes + 255) / 256 * 256; return q; };
@@ -1178,23 +1216,23 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
         if (R.idx) d.idx = (int *)take(n * K * sizeof(int));
         if (R.legs) d.legs = (double *)take(n * K * 4 * sizeof(double));
         if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_free[slot], 0));
-        rc = tofrt_table_dev(c, c->d_in + done, c->d_in + g + done, (long long)n, d_tof, d_kh, rec ? &d : nullptr,
-                             (void *)c->s_compute);
+        rc = table_dev_impl(c, c->d_in + done, c->d_in + g + done, (long long)n, d_tof, d_kh, rec ? &d : nullptr,
+                            (void *)c->s_compute, sh, 1);
         if (rc != TOFRT_OK) break;
         CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->s_compute));
         CUDA_TRY(cudaStreamWaitEvent(c->s_copy, c->ev_done[slot], 0));
         auto back = [&](void *dst, const void *src, size_t bytes) {
             return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->s_copy);
         };
-        CUDA_TRY(back(tof + done * E, d_tof, n * E * sizeof(double)));
-        CUDA_TRY(back(k_hit + done * E, d_kh, n * E * sizeof(int)));
-        if (R.pipe_x) CUDA_TRY(back(R.pipe_x + done * K, d.pipe_x, n * K * sizeof(double)));
-        if (R.pipe_z) CUDA_TRY(back(R.pipe_z + done * K, d.pipe_z, n * K * sizeof(double)));
-        if (R.lens2_x) CUDA_TRY(back(R.lens2_x + done * K, d.lens2_x, n * K * sizeof(double)));
-        if (R.lens2_z) CUDA_TRY(back(R.lens2_z + done * K, d.lens2_z, n * K * sizeof(double)));
-        if (R.target_x) CUDA_TRY(back(R.target_x + done * K, d.target_x, n * K * sizeof(double)));
-        if (R.idx) CUDA_TRY(back(R.idx + done * K, d.idx, n * K * sizeof(int)));
-        if (R.legs) CUDA_TRY(back(R.legs + done * K * 4, d.legs, n * K * 4 * sizeof(double)));
+        CUDA_TRY(back(tof + hbase * E, d_tof, n * E * sizeof(double)));
+        CUDA_TRY(back(k_hit + hbase * E, d_kh, n * E * sizeof(int)));
+        if (R.pipe_x) CUDA_TRY(back(R.pipe_x + hbase * K, d.pipe_x, n * K * sizeof(double)));
+        if (R.pipe_z) CUDA_TRY(back(R.pipe_z + hbase * K, d.pipe_z, n * K * sizeof(double)));
+        if (R.lens2_x) CUDA_TRY(back(R.lens2_x + hbase * K, d.lens2_x, n * K * sizeof(double)));
+        if (R.lens2_z) CUDA_TRY(back(R.lens2_z + hbase * K, d.lens2_z, n * K * sizeof(double)));
+        if (R.target_x) CUDA_TRY(back(R.target_x + hbase * K, d.target_x, n * K * sizeof(double)));
+        if (R.idx) CUDA_TRY(back(R.idx + hbase * K, d.idx, n * K * sizeof(int)));
+        if (R.legs) CUDA_TRY(back(R.legs + hbase * K * 4, d.legs, n * K * 4 * sizeof(double)));
         CUDA_TRY(cudaEventRecord(c->ev_free[slot], c->s_copy));
     }
     cudaError_t e1 = cudaStreamSynchronize(c->s_compute), e2 = cudaStreamSynchronize(c->s_copy);

@@ -41,6 +41,7 @@ class TofEngine:
         _capi.check(self._lib.tofrt_create(ctypes.byref(self._ctx), int(device)))
         self.device = int(device)
         self.K = self.E = 0
+        self.S, self.multi = 1, False
 
     def close(self):
         if getattr(self, "_ctx", None) and self._ctx.value:
@@ -56,19 +57,28 @@ class TofEngine:
     # ---- main_rt.py:449-479 -------------------------------------------------
     def setup(self, alpha, z_f, x_shooter, z_shooter, x_rx, c1=rs.C1, c2=rs.C2, l0=rs.L0, h0=rs.H0,
               d=None, rtol=1e-5, atol=1e-6):
+        """x_shooter / z_shooter: scalars (the reference: one shot, main_rt.py:481-482) or equal-length
+        arrays (full-matrix capture: every listed element shoots; tables gain a leading S axis)."""
         alpha, z_f, x_rx = _f64(alpha), _f64(z_f), _f64(x_rx)
         if alpha.ndim != 1 or z_f.shape != alpha.shape:
             raise ValueError("Coordinate arrays must have the same length.")
         l0, h0 = np.float64(l0), np.float64(h0)
         d = np.float64(l0 + h0) if d is None else np.float64(d)
         self.params = _capi.Params(float(c1), float(c2), float(l0), float(h0), float(d))
-        self.x_shooter, self.z_shooter = float(x_shooter), float(z_shooter)
+        self.multi = np.ndim(x_shooter) > 0
+        xs, zs = _f64(np.atleast_1d(x_shooter)), _f64(np.atleast_1d(z_shooter))
+        if xs.shape != zs.shape or xs.ndim != 1:
+            raise ValueError("x_shooter and z_shooter must have the same length")
+        self.x_shooter, self.z_shooter = xs, zs
         self.alpha, self.z_f, self.x_rx = alpha, z_f, x_rx
-        _capi.check(self._lib.tofrt_setup(
+        _capi.check(self._lib.tofrt_setup_shooters(
             self._ctx, ctypes.byref(self.params), alpha.ctypes.data, z_f.ctypes.data, len(alpha),
-            self.x_shooter, self.z_shooter, x_rx.ctypes.data, len(x_rx), float(rtol), float(atol)))
-        self.K, self.E = len(alpha), len(x_rx)
+            xs.ctypes.data, zs.ctypes.data, len(xs), x_rx.ctypes.data, len(x_rx), float(rtol), float(atol)))
+        self.K, self.E, self.S = len(alpha), len(x_rx), len(xs)
         return self
+
+    def _shape(self, G, last):
+        return (self.S, G, last) if self.multi else (G, last)
 
     def set_search(self, mode):
         """'guided' (default) or 'scan' (the reference's literal O(N) search); same results."""
@@ -110,15 +120,17 @@ class TofEngine:
         if radii.shape != offsets.shape:
             raise ValueError("radii and offsets must have the same length")
         G = len(radii)
-        tof = np.empty((G, self.E))
-        k_hit = np.empty((G, self.E), dtype=np.int32)
+        tof = np.empty(self._shape(G, self.E))
+        k_hit = np.empty(self._shape(G, self.E), dtype=np.int32)
         rec, out = None, {}
         if records:
             rec = _capi.RayRecords()
             for key in records:
                 if key not in RECORD_KEYS:
                     raise ValueError(f"unknown record {key!r}")
-                shape = (G, 4, self.K) if key == "legs" else (G, self.K)
+                shape = self._shape(G, 4 * self.K if key == "legs" else self.K)
+                if key == "legs":
+                    shape = shape[:-1] + (4, self.K)
                 out[key] = np.empty(shape, dtype=np.int32 if key == "idx" else np.float64)
                 setattr(rec, key, out[key].ctypes.data)
         _capi.check(self._lib.tofrt_table_host(self._ctx, radii.ctypes.data, offsets.ctypes.data, G,
@@ -136,13 +148,15 @@ class TofEngine:
             raise ValueError("radii/offsets must live on the engine's device and have the same shape")
         G = radii.numel()
         dev = radii.device
-        tof = out_tof if out_tof is not None else torch.empty((G, self.E), dtype=torch.float64, device=dev)
-        k_hit = out_k_hit if out_k_hit is not None else torch.empty((G, self.E), dtype=torch.int32, device=dev)
+        tof = out_tof if out_tof is not None else torch.empty(self._shape(G, self.E), dtype=torch.float64, device=dev)
+        k_hit = out_k_hit if out_k_hit is not None else torch.empty(self._shape(G, self.E), dtype=torch.int32, device=dev)
         rec, out = None, {}
         if records:
             rec = _capi.RayRecords()
             for key in records:
-                shape = (G, 4, self.K) if key == "legs" else (G, self.K)
+                shape = self._shape(G, self.K)
+                if key == "legs":
+                    shape = shape[:-1] + (4, self.K)
                 out[key] = torch.empty(shape, dtype=torch.int32 if key == "idx" else torch.float64, device=dev)
                 setattr(rec, key, out[key].data_ptr())
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -160,8 +174,8 @@ class TofEngine:
                 offsets.dtype == torch.float64 and radii.is_contiguous() and offsets.is_contiguous()):
             raise ValueError("radii/offsets must be contiguous float64 CUDA tensors")
         G, dev = radii.numel(), radii.device
-        tof = out_tof if out_tof is not None else torch.empty((G, self.E), dtype=torch.float32, device=dev)
-        k_hit = out_k_hit if out_k_hit is not None else torch.empty((G, self.E), dtype=torch.int32, device=dev)
+        tof = out_tof if out_tof is not None else torch.empty(self._shape(G, self.E), dtype=torch.float32, device=dev)
+        k_hit = out_k_hit if out_k_hit is not None else torch.empty(self._shape(G, self.E), dtype=torch.int32, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _capi.check(self._lib.tofrt_table_f32_dev(self._ctx, radii.data_ptr(), offsets.data_ptr(), G,
                                                   tof.data_ptr(), k_hit.data_ptr(), ctypes.c_void_p(stream)))

@@ -321,3 +321,35 @@ def test_fp32_mode_is_close_to_fp64(engine):
     dt = (t32.tof.double() - t64.tof)[same_ray].abs()
     assert float(dt.max()) < 5e-9 and float(dt.median()) < 5e-11  # measured 1.2e-9 / 5e-12
     assert bool(((t32.tof == 0) == (t32.k_hit < 0)).all())
+
+
+def test_full_matrix_capture_every_element_shoots(engine, golden, oracle_dm):
+    """S shooters per geometry in one call; each shooter's block equals the
+    single-shooter call and the oracle; the live reference pins the shooters it can run."""
+    x_a, z_a = rs.transducer()
+    alpha, zf = rs.launch_angles(), rs.focus_line()
+    p = oracle_dm.params()
+    rng = np.random.default_rng(21)
+    radii, offsets = rng.uniform(0.04, 0.1, 24), rng.uniform(-0.008, 0.008, 24)
+    engine.setup(alpha, zf, x_a, z_a, x_a)  # every element shoots: S = E = 65
+    t = engine.tof_table(radii, offsets, records=("idx",))
+    assert t.tof.shape == (65, 24, 65) and t.records["idx"].shape == (65, 24, 905)
+    for s in range(65):
+        tof, k_hit, idx = oracle_dm.table(p, radii, offsets, x_a[s], z_a[s], zf, alpha, x_a, want_idx=True)
+        assert np.array_equal(t.records["idx"][s], idx), s
+        assert np.array_equal(t.k_hit[s], k_hit.T) and np.array_equal(t.tof[s], tof.T), s
+    # device-resident API, same bytes
+    import torch
+    td = engine.tof_table_cuda(torch.from_numpy(radii).cuda(), torch.from_numpy(offsets).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(td.tof.cpu().numpy(), t.tof) and np.array_equal(td.k_hit.cpu().numpy(), t.k_hit)
+    # the live reference (tests/golden/shooters.npz)
+    sh = golden["shooters"]
+    t2 = engine.tof_table(sh["radius"], sh["offset"])
+    for i, s in enumerate(sh["shooter"]):
+        assert np.array_equal(t2.k_hit[s, i], sh["k_hit"][i])
+        assert np.abs(t2.tof[s, i] - sh["tof"][i]).max() <= TOF_TOL
+    # a single shooter given as a scalar keeps the 2-D layout
+    engine.setup(alpha, zf, x_a[7], z_a[7], x_a)
+    t1 = engine.tof_table(radii, offsets)
+    assert t1.tof.shape == (24, 65) and np.array_equal(t1.tof, t.tof[7]) and np.array_equal(t1.k_hit, t.k_hit[7])
