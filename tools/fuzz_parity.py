@@ -1,0 +1,53 @@
+"""Large differential runs (under gpurun), results summarised in profiles/fuzz_r1.json:
+ (1) GPU (guided) vs the CPU twin oracle, bit for bit, on random geometries over wide ranges;
+ (2) GPU guided vs GPU literal scan on millions of geometries (every output compared on device)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from ray_tracing_ultrasound_b200 import TofEngine, reference_setup as rs
+from oracle.oracle import Oracle
+
+out = {}
+x_a, z_a = rs.transducer(num_elements=128)
+alpha, zf = rs.launch_angles(), rs.focus_line()
+eng = TofEngine(0).setup(alpha, zf, x_a[64], z_a[64], x_a)
+o = Oracle(device_math=True); p = o.params()
+rng = np.random.default_rng(2024)
+
+# (1) vs the twin, including idx of every ray
+n1 = int(os.environ.get("FUZZ_ORACLE_GEOMS", "60000"))
+bad = 0; rays = 0; t0 = time.time()
+for lo in range(0, n1, 10000):
+    n = min(10000, n1 - lo)
+    radii = rng.uniform(0.002, 0.15, n); offsets = rng.uniform(-0.04, 0.04, n)
+    t = eng.tof_table(radii, offsets, records=("idx",))
+    tof, k_hit, idx = o.table(p, radii, offsets, x_a[64], z_a[64], zf, alpha, x_a, want_idx=True)
+    bad += int((t.records["idx"] != idx).sum()) + int((t.k_hit != k_hit.T).sum()) + int((t.tof != tof.T).sum())
+    rays += n * len(alpha)
+out["gpu_vs_twin_oracle"] = {"geometries": n1, "rays": rays, "table_entries": n1 * len(x_a), "mismatches": bad,
+                             "ranges": "r in [0.002, 0.15], offset in [-0.04, 0.04], E=129, K=N=905",
+                             "seconds": round(time.time() - t0, 1)}
+
+# (2) guided vs scan on device
+n2 = int(os.environ.get("FUZZ_MODE_GEOMS", "4000000"))
+mism = 0; fallback = 0; t0 = time.time()
+for lo in range(0, n2, 1000000):
+    n = min(1000000, n2 - lo)
+    r = torch.from_numpy(rng.uniform(0.002, 0.15, n)).cuda(); of = torch.from_numpy(rng.uniform(-0.04, 0.04, n)).cuda()
+    eng.set_search("guided"); a = eng.tof_table_cuda(r, of); torch.cuda.synchronize(); fallback += eng.last_stats()["scan_rays"]
+    eng.set_search("scan"); b = eng.tof_table_cuda(r, of); torch.cuda.synchronize()
+    mism += int((a.tof != b.tof).sum()) + int((a.k_hit != b.k_hit).sum())
+    del a, b
+out["guided_vs_scan"] = {"geometries": n2, "rays": n2 * len(alpha), "table_entries": n2 * len(x_a), "mismatches": mism,
+                         "rays_that_fell_back_to_the_scan": int(fallback), "seconds": round(time.time() - t0, 1)}
+# (2b) with per-ray idx on a smaller batch
+n3 = 200000
+r = torch.from_numpy(rng.uniform(0.002, 0.15, n3)).cuda(); of = torch.from_numpy(rng.uniform(-0.04, 0.04, n3)).cuda()
+eng.set_search("guided"); a = eng.tof_table_cuda(r, of, records=("idx", "target_x"))
+eng.set_search("scan"); b = eng.tof_table_cuda(r, of, records=("idx", "target_x"))
+torch.cuda.synchronize()
+ta, tb = a.records["target_x"], b.records["target_x"]
+out["guided_vs_scan_per_ray"] = {"geometries": n3, "rays": n3 * len(alpha),
+                                 "idx_mismatches": int((a.records["idx"] != b.records["idx"]).sum()),
+                                 "target_x_mismatches": int(((ta != tb) & ~(ta.isnan() & tb.isnan())).sum())}
+print(json.dumps(out, indent=1))
