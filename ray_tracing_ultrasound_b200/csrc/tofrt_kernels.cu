@@ -32,6 +32,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,7 @@ struct DevSetup {
     double rtol, atol, tol_max;              // np.isclose tolerances, and an upper bound of atol+rtol|x_e|
     double rx_min, rx_max;                   // finite receiver range
     int K, Npad, E, E_sorted, has_nonfinite_rx, tables_ok;
+    int hits_in_global;  // 1: E too large for the per-warp shared-memory first-hit state -> keep it in the output rows
     int shape;      // +1: sampled lens strictly concave in x, -1: strictly convex, 0: neither (no guided search)
     int guided;     // search mode: 1 = guided (bracketed) search, 0 = the reference's literal O(N) scan
     int log2n;      // ceil(log2(K)) + 1 bisection steps
@@ -219,6 +221,8 @@ __device__ __forceinline__ void chord_intersection(const double2 *lens, const do
 }
 
 // ---- the table kernel -----------------------------------------------------------
+// HG: first-hit state in the output rows (global memory) instead of warp-private shared memory
+template <bool HG>
 __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel(DevSetup S, TableArgs T)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -227,9 +231,9 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
     double2 *s_lens = reinterpret_cast<double2 *>(smem_raw);
     double2 *s_seg = s_lens + Npad;                  // [K-1] (+1 pad)
     double *s_xs = reinterpret_cast<double *>(s_seg + K);
-    double *s_tof = s_xs + S.E_sorted;               // [kWarps][E]
-    int *s_perm = reinterpret_cast<int *>(s_tof + (size_t)kWarps * E);
-    int *s_khit = s_perm + S.E_sorted;               // [kWarps][E]
+    double *s_tof = s_xs + S.E_sorted;               // [kWarps][E] (absent when HG)
+    int *s_perm = reinterpret_cast<int *>(s_tof + (HG ? (size_t)0 : (size_t)kWarps * E));
+    int *s_khit = s_perm + S.E_sorted;               // [kWarps][E] (absent when HG)
 
     for (int i = threadIdx.x; i < Npad; i += kThreads) s_lens[i] = S.lens[i];
     for (int i = threadIdx.x; i < K - 1; i += kThreads) s_seg[i] = S.seg[i];
@@ -237,8 +241,13 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *w_tof = s_tof + (size_t)warp * E;
-    int *w_khit = s_khit + (size_t)warp * E;
+    // first-hit state of the geometry this warp owns: warp-private shared memory, or (large E) the
+    // geometry's own output rows in global memory -- read back with volatile loads, because the
+    // atomicMin below happens in L2 and must not be shadowed by a stale L1 line
+    typedef typename std::conditional<HG, volatile double, double>::type tof_t;
+    typedef typename std::conditional<HG, volatile int, int>::type khit_t;
+    tof_t *w_tof = s_tof + (size_t)warp * E;
+    khit_t *w_khit = s_khit + (size_t)warp * E;
     const int nchunks = (K + 31) >> 5;
     const unsigned FULL = 0xffffffffu;
     unsigned st_rays = 0, st_scan_rays = 0, st_scan_warps = 0, st_onsample = 0;
@@ -253,6 +262,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
         const size_t sk = (size_t)(T.s_begin + w / T.G) * K;  // offset of the shooter's per-ray tables
         const double r_outer = T.radius[g], pipe_offset = T.offset[g];
         const double rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset;
+        if (HG) { w_tof = T.tof + (size_t)w * E; w_khit = T.k_hit + (size_t)w * E; }
         for (int e = lane; e < E; e += 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0; }
         __syncwarp();
 
@@ -476,11 +486,11 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                     hi = l;
                     while (hi < S.E_sorted && s_xs[hi] <= th) ++hi;
                     for (int i = lo; i < hi; ++i)
-                        if (np_isclose(target_x, s_xs[i], S.rtol, S.atol)) { atomicMin(&w_khit[s_perm[i]], k); mine = true; }
+                        if (np_isclose(target_x, s_xs[i], S.rtol, S.atol)) { atomicMin(const_cast<int *>(&w_khit[s_perm[i]]), k); mine = true; }
                 }
                 if (special) {
                     for (int e = 0; e < E; ++e)
-                        if (target_x == S.x_rx[e]) { atomicMin(&w_khit[e], k); mine = true; }
+                        if (target_x == S.x_rx[e]) { atomicMin(const_cast<int *>(&w_khit[e]), k); mine = true; }
                 }
                 __syncwarp();
                 if (mine || (want_legs && valid)) {
@@ -516,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
         __syncwarp();
         for (int e = lane; e < E; e += 32) {
             int kh = w_khit[e];
-            T.tof[(size_t)w * E + e] = w_tof[e];
+            if (!HG) T.tof[(size_t)w * E + e] = w_tof[e];
             T.k_hit[(size_t)w * E + e] = kh == kNoHit ? -1 : kh;
         }
         __syncwarp();
@@ -939,9 +949,14 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     S.rx_min = xs.empty() ? 1.0 : xs.front();
     S.rx_max = xs.empty() ? -1.0 : xs.back();
 
-    const size_t smem = (size_t)(S.Npad + K) * sizeof(double2) +
-                        (size_t)S.E_sorted * (sizeof(double) + sizeof(int)) +
-                        (size_t)kWarps * E * (sizeof(double) + sizeof(int)) + 16;
+    const size_t smem_tables = (size_t)(S.Npad + K) * sizeof(double2) +
+                               (size_t)S.E_sorted * (sizeof(double) + sizeof(int)) + 16;
+    size_t smem = smem_tables + (size_t)kWarps * E * (sizeof(double) + sizeof(int));
+    S.hits_in_global = 0;
+    if (smem > 227 * 1024) {  // many receivers: the per-warp first-hit state moves to the output rows
+        S.hits_in_global = 1;
+        smem = smem_tables;
+    }
     if (smem > 227 * 1024)
         return fail(TOFRT_E_TOOLARGE, "tofrt_setup: K/E need " + std::to_string(smem) + " B of shared memory (> 227 KB)");
 
@@ -1036,14 +1051,20 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
         c->SF = F;
         c->smem_f32 = (size_t)2 * K * sizeof(float2) + (size_t)S.E_sorted * (sizeof(float) + sizeof(int)) +
                       (size_t)kWarps * E * (sizeof(float) + sizeof(int)) + 16;
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)c->smem_f32));
+        if (c->smem_f32 > 227 * 1024) c->smem_f32 = 0;  // FP32 mode keeps its first-hit state in shared memory only
+        else
+            CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)c->smem_f32));
         CUDA_TRY(cudaDeviceSynchronize());
     }
 
-    CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (S.hits_in_global)
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel, kThreads, smem));
+    if (S.hits_in_global) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<true>, kThreads, smem));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<false>, kThreads, smem));
     c->ctas_per_sm = std::max(1, occ);
     c->S = S; c->K = K; c->E = E; c->smem = smem; c->n_shooters = NS;
     c->ready = true;
@@ -1110,7 +1131,8 @@ static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_
     CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
     long long warps_needed = G * s_count;
     int grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, (warps_needed + kWarps - 1) / kWarps);
-    tofrt_table_kernel<<<grid, kThreads, c->smem, st>>>(c->S, T);
+    if (c->S.hits_in_global) tofrt_table_kernel<true><<<grid, kThreads, c->smem, st>>>(c->S, T);
+    else tofrt_table_kernel<false><<<grid, kThreads, c->smem, st>>>(c->S, T);
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
 }
@@ -1128,6 +1150,7 @@ int tofrt_table_f32_dev(tofrt_ctx *c, const double *d_radius, const double *d_of
     if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_table_f32_dev: call tofrt_setup first");
     if (G == 0) return TOFRT_OK;
     if (!d_radius || !d_offset || !d_tof || !d_k_hit) return fail(TOFRT_E_BADARG, "tofrt_table_f32_dev: NULL buffer");
+    if (c->smem_f32 == 0) return fail(TOFRT_E_TOOLARGE, "tofrt_table_f32_dev: too many receivers for the FP32 mode");
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     TableArgsF T{};
@@ -1277,7 +1300,7 @@ int tofrt_kernel_info(tofrt_ctx *c, int *grid, int *block, int *smem_bytes, int 
 {
     if (!c) return fail(TOFRT_E_BADARG, "tofrt_kernel_info: ctx is NULL");
     cudaFuncAttributes fa{};
-    CUDA_TRY(cudaFuncGetAttributes(&fa, tofrt_table_kernel));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, tofrt_table_kernel<false>));
     if (grid) *grid = c->sm_count * c->ctas_per_sm;
     if (block) *block = kThreads;
     if (smem_bytes) *smem_bytes = (int)c->smem;

@@ -353,3 +353,28 @@ def test_full_matrix_capture_every_element_shoots(engine, golden, oracle_dm):
     engine.setup(alpha, zf, x_a[7], z_a[7], x_a)
     t1 = engine.tof_table(radii, offsets)
     assert t1.tof.shape == (24, 65) and np.array_equal(t1.tof, t.tof[7]) and np.array_equal(t1.k_hit, t.k_hit[7])
+
+
+@pytest.mark.parametrize("n_elements", [1024, 4096])
+def test_many_receivers(engine, oracle_dm, n_elements):
+    """More receivers than the per-warp shared-memory first-hit state can hold (BASELINE config 5 has
+    1 025): the state moves into the output rows; results stay bit-identical to the oracle."""
+    x_a, z_a = rs.transducer(num_elements=n_elements, pitch=np.float64(0.04 / n_elements))
+    alpha, zf = rs.launch_angles(), rs.focus_line()
+    engine.setup(alpha, zf, x_a[n_elements // 2], z_a[0], x_a, atol=1e-5)
+    rng = np.random.default_rng(n_elements)
+    radii, offsets = rng.uniform(0.01, 0.1, 40), rng.uniform(-0.01, 0.01, 40)
+    p = oracle_dm.params()
+    tof, k_hit, _ = oracle_dm.table(p, radii, offsets, x_a[n_elements // 2], z_a[0], zf, alpha, x_a, atol=1e-5)
+    for mode in ("guided", "scan"):
+        engine.set_search(mode)
+        t = engine.tof_table(radii, offsets)
+        assert t.tof.shape == (40, n_elements + 1)
+        assert int(t.hit.sum()) > 500
+        assert np.array_equal(t.k_hit, k_hit.T) and np.array_equal(t.tof, tof.T)
+    engine.set_search("guided")
+    from ray_tracing_ultrasound_b200 import TofrtError
+    import torch
+    if n_elements >= 4096:
+        with pytest.raises(TofrtError):
+            engine.tof_table_f32_cuda(torch.from_numpy(radii).cuda(), torch.from_numpy(offsets).cuda())
