@@ -131,6 +131,18 @@ int tofrt_table_host(tofrt_ctx *ctx, const double *radius, const double *offset,
 int tofrt_table_f32_dev(tofrt_ctx *ctx, const double *d_radius, const double *d_offset, long long G,
                         float *d_tof, int *d_k_hit, void *stream);
 
+/* Two-point Fermat solve (no function of the reference corresponds to it --
+ * parity unpinned, checked against a NumPy/SciPy oracle and analytic known answers).  For every
+ * (receiver e at (x_rx[e], d), focal point (fx[f], fz[f]) below the lens) pair: the lens entry
+ * point minimising |A_e - P(alpha)|/c1 + |P(alpha) - F|/c2 over the lens of the current setup
+ * (h_from_alpha / dh_from_alpha, main_rt.py:180-214): kmin = discrete argmin over the lens
+ * samples, tof = travel time at the refined stationary point, alpha = refined entry angle
+ * (may be NULL).  Element-major outputs: tof[e*F + f]. */
+int tofrt_fermat_dev(tofrt_ctx *ctx, const double *d_fx, const double *d_fz, long long F, double *d_tof,
+                     int *d_kmin, double *d_alpha, void *stream);
+int tofrt_fermat_host(tofrt_ctx *ctx, const double *fx, const double *fz, long long F, double *tof,
+                      int *kmin, double *alpha);
+
 /* Roofline denominator, measured on the device the context lives on: FP64
  * instructions per second (thread-level) of a DFMA stream and of the un-fused
  * DMUL+DADD stream the search loop issues (SURVEY.md section 8 d). */

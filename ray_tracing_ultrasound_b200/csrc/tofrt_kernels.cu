@@ -768,6 +768,119 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
     }
 }
 
+// =====================================================================================
+// Two-point Fermat solve (SURVEY.md row f4 -- BASELINE.json north_star's literal wording).
+// For every (array element e, focal point F) pair: the lens entry point P(alpha) that minimises
+//     t(alpha) = |A_e - P(alpha)| / c1 + |P(alpha) - F| / c2
+// over the lens surface of the current setup -- discrete argmin over the N lens samples, then a
+// safeguarded secant (Illinois) iteration on dt/dalpha inside the two neighbouring sample
+// intervals, using the reference's own h(alpha), dh/dalpha (main_rt.py:180-234).  The reference
+// has no such function: parity is unpinned; the checker is a NumPy/SciPy oracle plus analytic
+// known answers (tests/test_gpu_fermat.py).
+// One CTA works on (element e, 256 focal points) items; the lens samples and the element's
+// |A_e - P_j|/c1 row are staged in shared memory and broadcast to the 256 threads.
+// =====================================================================================
+constexpr int kFermatThreads = 256;
+
+struct FermatArgs {
+    const double *fx, *fz;   // [F] focal points
+    long long F;
+    const double *d1;        // [E][N]  |A_e - P_j| / c1
+    const double *alpha;     // [N]
+    double *tof;             // [E][F]
+    int *kmin;               // [E][F]
+    double *alpha_out;       // [E][F] or null
+    double z_el;             // array line
+    unsigned long long *counter;
+};
+
+__global__ void tofrt_fermat_d1_kernel(DevSetup S, double z_el, double *d1)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int e = blockIdx.y;
+    if (j >= S.K) return;
+    double2 p = S.lens[j];
+    d1[(size_t)e * S.K + j] = dist2d(S.x_rx[e], z_el, p.x, p.y) / S.c1;
+}
+
+// t(alpha) and dt/dalpha at a continuous lens angle
+__device__ __forceinline__ void fermat_eval(const DevSetup &S, double al, double ax, double az, double fx, double fz,
+                                            double *t, double *dt)
+{
+    double sn, cs, h, dz, dx;
+    tofrt_sincos(al, &sn, &cs);
+    lens_point(S, sn, cs, &h, &dz, &dx);
+    double px = h * sn, pz = h * cs;
+    double u1x = px - ax, u1z = pz - az, u2x = px - fx, u2z = pz - fz;
+    double r1 = sqrt(u1x * u1x + u1z * u1z), r2 = sqrt(u2x * u2x + u2z * u2z);
+    *t = r1 / S.c1 + r2 / S.c2;
+    *dt = (u1x * dx + u1z * dz) / (S.c1 * r1) + (u2x * dx + u2z * dz) / (S.c2 * r2);
+}
+
+__global__ void __launch_bounds__(kFermatThreads) tofrt_fermat_kernel(DevSetup S, FermatArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = S.K;
+    double2 *s_lens = reinterpret_cast<double2 *>(smem_raw);
+    double *s_d1 = reinterpret_cast<double *>(s_lens + N);
+    __shared__ unsigned long long s_item;
+    for (int i = threadIdx.x; i < N; i += kFermatThreads) s_lens[i] = S.lens[i];
+    const long long tiles = (A.F + kFermatThreads - 1) / kFermatThreads;
+    const unsigned long long items = (unsigned long long)tiles * S.E;
+    const double inv_c2 = 1.0 / S.c2;
+    int cur_e = -1;
+    for (;;) {
+        __syncthreads();  // previous item done with s_d1 / s_item
+        if (threadIdx.x == 0) s_item = atomicAdd(A.counter, 1ull);
+        __syncthreads();
+        const unsigned long long item = s_item;
+        if (item >= items) break;
+        const int e = (int)(item / tiles);
+        const long long f = (long long)(item % tiles) * kFermatThreads + threadIdx.x;
+        if (e != cur_e) {  // uniform across the CTA
+            for (int i = threadIdx.x; i < N; i += kFermatThreads) s_d1[i] = A.d1[(size_t)e * N + i];
+            cur_e = e;
+            __syncthreads();
+        }
+        if (f >= A.F) continue;
+        const double fx = A.fx[f], fz = A.fz[f];
+        const double ax = S.x_rx[e], az = A.z_el;
+        // ---- discrete argmin over the sampled surface (first minimum on ties) ----
+        double best = INFINITY;
+        int jbest = 0;
+#pragma unroll 4
+        for (int j = 0; j < N; ++j) {
+            const double2 p = s_lens[j];
+            const double ux = p.x - fx, uz = p.y - fz;
+            const double t = fma(sqrt(fma(ux, ux, uz * uz)), inv_c2, s_d1[j]);
+            if (t < best) { best = t; jbest = j; }
+        }
+        // ---- continuous refinement between the neighbouring samples ----
+        double a = A.alpha[max(jbest - 1, 0)], b = A.alpha[min(jbest + 1, N - 1)];
+        double ta, ga, tb, gb, tc, gc;
+        fermat_eval(S, a, ax, az, fx, fz, &ta, &ga);
+        fermat_eval(S, b, ax, az, fx, fz, &tb, &gb);
+        double al = A.alpha[jbest], tof;
+        fermat_eval(S, al, ax, az, fx, fz, &tof, &gc);
+        if (ga < 0.0 && gb > 0.0) {  // a bracketed stationary point: Illinois false position on dt/dalpha
+            int side = 0;
+            for (int it = 0; it < 8; ++it) {
+                double c = (a * gb - b * ga) / (gb - ga);
+                if (!(c > a && c < b)) c = 0.5 * (a + b);
+                fermat_eval(S, c, ax, az, fx, fz, &tc, &gc);
+                al = c; tof = tc;
+                if (gc == 0.0) break;
+                if (gc > 0.0) { b = c; gb = gc; if (side == 1) ga *= 0.5; side = 1; }
+                else { a = c; ga = gc; if (side == -1) gb *= 0.5; side = -1; }
+            }
+        }
+        const size_t o = (size_t)e * A.F + f;
+        A.tof[o] = tof;
+        A.kmin[o] = jbest;
+        if (A.alpha_out) A.alpha_out[o] = al;
+    }
+}
+
 // ---- FP64 issue-rate micro-benchmark (the roofline denominator, measured on the box) ----
 // 8 independent dependency chains per thread; MODE 0: DFMA, MODE 1: DMUL+DADD (un-fused, as
 // the scan issues them).  Each loop iteration issues 16 FP64 instructions per thread.
@@ -815,6 +928,7 @@ struct tofrt_ctx {
     bool ready = false;
     DevSetup S{};
     int K = 0, E = 0;
+    double params_d = 0.0;   // array line z = d
     size_t smem = 0;
     int ctas_per_sm = 1;
     // device buffers owned by the context
@@ -834,6 +948,7 @@ struct tofrt_ctx {
     void *ws[2] = {nullptr, nullptr};
     size_t ws_bytes = 0, in_cap = 0;
     double *d_in = nullptr;
+    double *d_d1 = nullptr;   // Fermat solver: |A_e - P_j|/c1, built lazily per setup
     void free_all()
     {
         cudaFree(d_alpha); cudaFree(d_zf); cudaFree(d_a); cudaFree(d_b); cudaFree(d_phi); cudaFree(d_leg1);
@@ -879,7 +994,7 @@ int tofrt_destroy(tofrt_ctx *c)
     cudaSetDevice(c->device);
     c->free_all();
     cudaFree(c->d_counter);
-    cudaFree(c->ws[0]); cudaFree(c->ws[1]); cudaFree(c->d_in);
+    cudaFree(c->ws[0]); cudaFree(c->ws[1]); cudaFree(c->d_in); cudaFree(c->d_d1);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
@@ -909,6 +1024,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     CUDA_TRY(cudaSetDevice(c->device));
     c->ready = false;
     c->free_all();
+    cudaFree(c->d_d1); c->d_d1 = nullptr;
     CUDA_TRY(cudaMalloc(&c->d_bad, sizeof(int)));
 
     DevSetup S{};
@@ -1066,7 +1182,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     if (S.hits_in_global) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<true>, kThreads, smem));
     else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<false>, kThreads, smem));
     c->ctas_per_sm = std::max(1, occ);
-    c->S = S; c->K = K; c->E = E; c->smem = smem; c->n_shooters = NS;
+    c->S = S; c->K = K; c->E = E; c->smem = smem; c->n_shooters = NS; c->params_d = p->d;
     c->ready = true;
     return TOFRT_OK;
 }
@@ -1262,6 +1378,66 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
     if (rc != TOFRT_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess)
         return fail(TOFRT_E_CUDA, std::string("tofrt_table_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return TOFRT_OK;
+}
+
+int tofrt_fermat_dev(tofrt_ctx *c, const double *d_fx, const double *d_fz, long long F, double *d_tof, int *d_kmin,
+                     double *d_alpha, void *stream)
+{
+    if (!c || F < 0) return fail(TOFRT_E_BADARG, "tofrt_fermat_dev: bad argument");
+    if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_fermat_dev: call tofrt_setup first");
+    if (F == 0) return TOFRT_OK;
+    if (!d_fx || !d_fz || !d_tof || !d_kmin) return fail(TOFRT_E_BADARG, "tofrt_fermat_dev: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int K = c->K, E = c->E;
+    const size_t smem = (size_t)K * (sizeof(double2) + sizeof(double)) + 16;
+    if (smem > 227 * 1024) return fail(TOFRT_E_TOOLARGE, "tofrt_fermat_dev: too many lens samples");
+    if (!c->d_d1) {
+        CUDA_TRY(cudaMalloc(&c->d_d1, sizeof(double) * (size_t)K * E));
+        dim3 grid((K + 127) / 128, E);
+        tofrt_fermat_d1_kernel<<<grid, 128, 0, st>>>(c->S, c->params_d, c->d_d1);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_fermat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    FermatArgs A{};
+    A.fx = d_fx; A.fz = d_fz; A.F = F; A.d1 = c->d_d1; A.alpha = c->d_alpha; A.tof = d_tof; A.kmin = d_kmin;
+    A.alpha_out = d_alpha; A.z_el = c->params_d; A.counter = c->d_counter;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_fermat_kernel, kFermatThreads, smem));
+    const long long items = ((F + kFermatThreads - 1) / kFermatThreads) * E;
+    int grid = (int)std::min<long long>((long long)c->sm_count * std::max(1, occ), items);
+    tofrt_fermat_kernel<<<grid, kFermatThreads, smem, st>>>(c->S, A);
+    CUDA_TRY(cudaGetLastError());
+    return TOFRT_OK;
+}
+
+int tofrt_fermat_host(tofrt_ctx *c, const double *fx, const double *fz, long long F, double *tof, int *kmin,
+                      double *alpha)
+{
+    if (!c || F < 0) return fail(TOFRT_E_BADARG, "tofrt_fermat_host: bad argument");
+    if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_fermat_host: call tofrt_setup first");
+    if (F == 0) return TOFRT_OK;
+    if (!fx || !fz || !tof || !kmin) return fail(TOFRT_E_BADARG, "tofrt_fermat_host: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = (size_t)F, EF = n * c->E;
+    double *d_f = nullptr, *d_t = nullptr, *d_a = nullptr;
+    int *d_k = nullptr;
+    cudaError_t e = cudaMalloc(&d_f, sizeof(double) * 2 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_t, sizeof(double) * EF);
+    if (e == cudaSuccess) e = cudaMalloc(&d_k, sizeof(int) * EF);
+    if (e == cudaSuccess && alpha) e = cudaMalloc(&d_a, sizeof(double) * EF);
+    if (e == cudaSuccess) e = cudaMemcpy(d_f, fx, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_f + n, fz, sizeof(double) * n, cudaMemcpyHostToDevice);
+    int rc = TOFRT_OK;
+    if (e == cudaSuccess) rc = tofrt_fermat_dev(c, d_f, d_f + n, F, d_t, d_k, d_a, nullptr);
+    if (e == cudaSuccess && rc == TOFRT_OK) e = cudaMemcpy(tof, d_t, sizeof(double) * EF, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == TOFRT_OK) e = cudaMemcpy(kmin, d_k, sizeof(int) * EF, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == TOFRT_OK && alpha) e = cudaMemcpy(alpha, d_a, sizeof(double) * EF, cudaMemcpyDeviceToHost);
+    cudaFree(d_f); cudaFree(d_t); cudaFree(d_k); cudaFree(d_a);
+    if (rc != TOFRT_OK) return rc;
+    if (e != cudaSuccess) return fail(TOFRT_E_CUDA, std::string("tofrt_fermat_host: ") + cudaGetErrorString(e));
     return TOFRT_OK;
 }
 

@@ -181,6 +181,37 @@ class TofEngine:
                                                   tof.data_ptr(), k_hit.data_ptr(), ctypes.c_void_p(stream)))
         return TofTable(tof, k_hit)
 
+    # ---- two-point Fermat solve (extension; parity unpinned) ---------------
+    def fermat_tof(self, fx, fz, with_alpha=False):
+        """One-way travel time element -> lens -> focal point for every (receiver, focal point) pair:
+        returns (tof[E, F], kmin[E, F][, alpha[E, F]]), host arrays."""
+        fx, fz = _f64(fx).ravel(), _f64(fz).ravel()
+        if fx.shape != fz.shape:
+            raise ValueError("fx and fz must have the same length")
+        F = len(fx)
+        tof = np.empty((self.E, F))
+        kmin = np.empty((self.E, F), dtype=np.int32)
+        alpha = np.empty((self.E, F)) if with_alpha else None
+        _capi.check(self._lib.tofrt_fermat_host(self._ctx, fx.ctypes.data, fz.ctypes.data, F, tof.ctypes.data,
+                                                kmin.ctypes.data, alpha.ctypes.data if with_alpha else None))
+        return (tof, kmin, alpha) if with_alpha else (tof, kmin)
+
+    def fermat_tof_cuda(self, fx, fz, with_alpha=False):
+        """Same, device-resident torch tensors, asynchronous on the current stream."""
+        import torch
+        if not (fx.is_cuda and fz.is_cuda and fx.dtype == torch.float64 and fz.dtype == torch.float64 and
+                fx.is_contiguous() and fz.is_contiguous() and fx.shape == fz.shape):
+            raise ValueError("fx/fz must be contiguous float64 CUDA tensors of the same shape")
+        F, dev = fx.numel(), fx.device
+        tof = torch.empty((self.E, F), dtype=torch.float64, device=dev)
+        kmin = torch.empty((self.E, F), dtype=torch.int32, device=dev)
+        alpha = torch.empty((self.E, F), dtype=torch.float64, device=dev) if with_alpha else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _capi.check(self._lib.tofrt_fermat_dev(self._ctx, fx.data_ptr(), fz.data_ptr(), F, tof.data_ptr(),
+                                               kmin.data_ptr(), alpha.data_ptr() if with_alpha else None,
+                                               ctypes.c_void_p(stream)))
+        return (tof, kmin, alpha) if with_alpha else (tof, kmin)
+
     # ---- main_rt.py:337-441 -----------------------------------------------------
     def shoot_rays(self, r_outer, pipe_offset, with_idx=False, with_legs=False):
         recs = ["pipe_x", "pipe_z", "lens2_x", "lens2_z", "target_x"]
