@@ -656,32 +656,38 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
             const bool fin = valid && fabsf(m) < 1e18f && fabsf(b) < 1e18f;
             int idx = -1;
             bool need_scan = fin, check_on_sample = false;
-            if (fin && S.shape != 0) {
+            if (S.shape != 0) {  // the guided search of the FP64 kernel, in float (tol = 2^-19 (...))
                 const float sh = (float)S.shape;
                 const float tol = (fabsf(m) * S.X + fabsf(b) + S.Z) * 1.9073486328125e-06f /* 2^-19 */ + 1e-30f;
                 const float g0 = sh * line_diff_f(s_lens[0], m, b), gN = sh * line_diff_f(s_lens[N - 1], m, b);
-                int lo = 0, hi = 0;
+                const bool pos0 = g0 > tol, neg0 = g0 < -tol;
                 bool bracket = false, none = false;
                 float edge = 0.f;
-                if (g0 > tol) {
-                    if (gN > tol) { none = true; edge = fminf(g0, gN) - tol; }
-                    else { bracket = true; hi = N - 1; }
-                } else if (g0 < -tol) {
-                    const float ms = sh * m;
-                    int l = 0, r = N - 1;
-                    while (l < r) { int mid = (l + r) >> 1; if (sh * s_seg[min(mid, N - 2)].x > ms) l = mid + 1; else r = mid; }
-                    const float gm = sh * line_diff_f(s_lens[l], m, b);
-                    if (gm < -tol) { none = true; edge = -gm - tol; }
-                    else if (gm > tol) { bracket = true; hi = l; }
+                if (fin && pos0 && gN > tol) { none = true; edge = fminf(g0, gN) - tol; }
+                else if (fin && (pos0 || neg0)) bracket = true;
+                const float sgn = pos0 ? sh : -sh;
+                const float ms_eff = pos0 ? -INFINITY : sh * m;
+                int lo = 0, hi = N - 1;
+                for (int it = 0; it < S.log2n; ++it) {
+                    const int mid = (lo + hi) >> 1;
+                    const bool cond = (sgn * line_diff_f(s_lens[mid], m, b) > tol) && (sh * s_seg[mid].x > ms_eff);
+                    const bool act = bracket && (hi - lo > 1);
+                    lo = (act && cond) ? mid : lo;
+                    hi = (act && !cond) ? mid : hi;
+                }
+                if (bracket && neg0) {
+                    const float ghi = sh * line_diff_f(s_lens[hi], m, b);
+                    if (ghi < -tol) { bracket = false; none = true; edge = -ghi - tol; }
                 }
                 if (bracket) {
-                    const bool pos0 = g0 > 0;
-                    while (hi - lo > 1) {
-                        int mid = (lo + hi) >> 1;
-                        float gmid = sh * line_diff_f(s_lens[mid], m, b);
-                        if (pos0 ? (gmid > tol) : (gmid < -tol)) lo = mid; else hi = mid;
+                    int cprev = sign_class_f(line_diff_f(s_lens[lo], m, b));
+                    int j = lo;
+                    for (; j + 1 < N; ++j) {
+                        int cnext = sign_class_f(line_diff_f(s_lens[j + 1], m, b));
+                        if (class_change(cprev, cnext)) break;
+                        cprev = cnext;
                     }
-                    idx = scan_exact_from_f(s_lens, N, m, b, lo);
+                    if (j + 1 < N) idx = j;
                     need_scan = false;
                     check_on_sample = idx < 0;
                 } else if (none) {
@@ -708,8 +714,8 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
                 for (int j = 0; j < N; ++j)
                     if (fabsf(line_diff_f(s_lens[j], m, b)) <= 1e-8f) { ix = s_lens[j].x; iz = s_lens[j].y; break; }
             }
-            float target_x;
-            {
+            float target_x = NAN;
+            if (__any_sync(FULL, valid && ix == ix)) {
                 float alpha_i = atan2f(ix, iz);
                 float sn, cs;
                 sincosf(alpha_i, &sn, &cs);
@@ -722,11 +728,14 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
                 float dz = dh * cs - hh * sn, dx = dh * sn + hh * cs;
                 float phi_slope = atan2f(dz, dx);
                 float theta_1 = phi_l - (phi_slope + HALF_PI_F);
-                float theta_2 = asinf(S.c1_over_c2 * sinf(theta_1));
-                float phi_last = phi_slope - HALF_PI_F + theta_2;
-                float a_i = tanf(phi_last);
-                float b_i = iz - a_i * ix;
-                target_x = (z_f - b_i) / a_i;
+                float s_arg = S.c1_over_c2 * sinf(theta_1);
+                if (__any_sync(FULL, valid && fabsf(s_arg) <= 1.0f)) {
+                    float theta_2 = asinf(s_arg);
+                    float phi_last = phi_slope - HALF_PI_F + theta_2;
+                    float a_i = tanf(phi_last);
+                    float b_i = iz - a_i * ix;
+                    target_x = (z_f - b_i) / a_i;
+                }
             }
             bool cand = valid && target_x >= S.rx_min - S.tol_max && target_x <= S.rx_max + S.tol_max;
             bool special = valid && S.has_nonfinite_rx && isinf(target_x);
