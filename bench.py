@@ -235,6 +235,32 @@ def main():
     e2e_value = E * G * world * e2e_steps / float(te.item())
     parity_ok = bool(torch.equal(tof_h, tof_d.cpu()) and torch.equal(kh_h, kh_d.cpu()))
 
+    # ---- e2e, sparse form: same pass, host gets only the hits (tofrt_hits_host) ----
+    n_hits_dense = int((kh_d >= 0).sum())
+    cap = n_hits_dense + 1024
+    hb = (torch.empty(cap, dtype=torch.int32).pin_memory(), torch.empty(cap, dtype=torch.int32).pin_memory(),
+          torch.empty(cap, dtype=torch.int32).pin_memory(), torch.empty(cap, dtype=torch.float64).pin_memory())
+    import ctypes as _ct
+    n_hits = _ct.c_longlong(0)
+
+    def hits_step():
+        _capi.check(eng._lib.tofrt_hits_host(eng._ctx, r_h.data_ptr(), o_h.data_ptr(), G, cap, hb[0].data_ptr(),
+                                             hb[1].data_ptr(), hb[2].data_ptr(), hb[3].data_ptr(), _ct.byref(n_hits)))
+
+    hits_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hits_step()
+    barrier()
+    th = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    hits_value = E * G * world * e2e_steps / float(th.item())
+    nh = int(n_hits.value)
+    hits_ok = bool(nh == n_hits_dense and torch.equal(
+        hb[3][:nh], tof_h[hb[0][:nh].long(), hb[1][:nh].long()]))
+
     # ---- the other search mode, device-resident, for the roofline discussion ----
     other = "scan" if args.search == "guided" else "guided"
     eng.set_search(other)
@@ -341,7 +367,11 @@ def main():
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(G * 16 * world),
                     "d2h_bytes_per_step": int(G * E * 12 * world), "steps": e2e_steps,
-                    "matches_device_path": parity_ok},
+                    "matches_device_path": parity_ok,
+                    "sparse_hits": {"value": hits_value, "unit": UNIT, "d2h_bytes_per_step": int(nh * 20 * world),
+                                    "hits_per_step": nh * world, "matches_dense": hits_ok,
+                                    "note": "same pass through tofrt_hits_host: the host receives only the "
+                                            "(row, receiver, ray, tof) list of the hits (2 % of the entries)"}},
             "gpu_launches": args.steps * 1,
             "roofline": roofline,
         }

@@ -125,6 +125,15 @@ int tofrt_table_dev(tofrt_ctx *ctx, const double *d_radius, const double *d_offs
 int tofrt_table_host(tofrt_ctx *ctx, const double *radius, const double *offset, long long G,
                      double *tof, int *k_hit, const tofrt_ray_records *rec);
 
+/* Sparse form of tofrt_table_host: only the hits (k_hit >= 0), ordered by (row, receiver), where
+ * row = geometry index (shooter * G + geometry with several shooters).  The dense table is
+ * 97-98 % misses; the list cuts the device->host traffic ~30x.  If more than `capacity` hits
+ * exist, the first `capacity` are returned, *n_hits holds the total and the call returns
+ * TOFRT_E_TOOLARGE.  Same rows as main_rt.py:487-504 writes with hitted == True. */
+int tofrt_hits_host(tofrt_ctx *ctx, const double *radius, const double *offset, long long G,
+                    long long capacity, int *hit_g, int *hit_e, int *hit_k, double *hit_tof,
+                    long long *n_hits);
+
 /* FP32 mode of tofrt_table_dev (reported separately, no bit-parity claim): the same
  * pipeline with the per-ray arithmetic in float; tof is float[G][E].  radius/offset stay
  * double arrays so both modes share their inputs. */

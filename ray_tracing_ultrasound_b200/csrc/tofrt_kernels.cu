@@ -26,6 +26,7 @@
 // Compile with -fmad=false: the only fused operations are the explicit fma()
 // calls inside tofrt_math.h (shared bit-for-bit with the oracle's twin build).
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -890,6 +891,44 @@ __global__ void __launch_bounds__(kFermatThreads) tofrt_fermat_kernel(DevSetup S
     }
 }
 
+// ---- sparse form of the table: only the hits, ordered by (row, receiver) -------------------
+// 97-98 % of the table entries are misses; a consumer on the host that only wants the hits gets
+// them as a list, which cuts the device->host traffic ~30x (the dense D2H is what limits the
+// end-to-end rate once 8 GPUs share the host's PCIe/memory bandwidth).  Deterministic: count per
+// row, exclusive scan, ordered compaction (no atomics).
+__global__ void tofrt_count_hits_kernel(const int *k_hit, long long rows, int E, long long *cnt)
+{
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    int n = 0;
+    for (int e = lane; e < E; e += 32) n += k_hit[row * E + e] >= 0;
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) cnt[row] = n;
+}
+
+__global__ void tofrt_compact_hits_kernel(const int *k_hit, const double *tof, long long rows, int E,
+                                          const long long *off, long long row0, long long base, long long capacity,
+                                          int *hit_g, int *hit_e, int *hit_k, double *hit_tof)
+{
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    long long o = base + off[row];
+    for (int e0 = 0; e0 < E; e0 += 32) {
+        const int e = e0 + lane;
+        const int kh = e < E ? k_hit[row * E + e] : -1;
+        const unsigned m = __ballot_sync(0xffffffffu, kh >= 0);
+        if (kh >= 0) {
+            const long long i = o + __popc(m & ((1u << lane) - 1u));
+            if (i < capacity) {
+                hit_g[i] = (int)(row0 + row); hit_e[i] = e; hit_k[i] = kh; hit_tof[i] = tof[row * E + e];
+            }
+        }
+        o += __popc(m);
+    }
+}
+
 // ---- FP64 issue-rate micro-benchmark (the roofline denominator, measured on the box) ----
 // 8 independent dependency chains per thread; MODE 0: DFMA, MODE 1: DMUL+DADD (un-fused, as
 // the scan issues them).  Each loop iteration issues 16 FP64 instructions per thread.
@@ -957,6 +996,9 @@ struct tofrt_ctx {
     void *ws[2] = {nullptr, nullptr};
     size_t ws_bytes = 0, in_cap = 0;
     double *d_in = nullptr;
+    // tofrt_hits_host workspace (grow-only): dense intermediate, counts/offsets, scan scratch, hit list
+    void *hw[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t hw_bytes[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double *d_d1 = nullptr;   // Fermat solver: |A_e - P_j|/c1, built lazily per setup
     void free_all()
     {
@@ -1004,6 +1046,7 @@ int tofrt_destroy(tofrt_ctx *c)
     c->free_all();
     cudaFree(c->d_counter);
     cudaFree(c->ws[0]); cudaFree(c->ws[1]); cudaFree(c->d_in); cudaFree(c->d_d1);
+    for (int i = 0; i < 10; ++i) cudaFree(c->hw[i]);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
@@ -1387,6 +1430,89 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
     if (rc != TOFRT_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess)
         return fail(TOFRT_E_CUDA, std::string("tofrt_table_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return TOFRT_OK;
+}
+
+int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, long long G, long long capacity,
+                    int *hit_g, int *hit_e, int *hit_k, double *hit_tof, long long *n_hits)
+{
+    if (!c || G < 0 || capacity < 0 || !n_hits) return fail(TOFRT_E_BADARG, "tofrt_hits_host: bad argument");
+    if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_hits_host: call tofrt_setup first");
+    *n_hits = 0;
+    if (G == 0) return TOFRT_OK;
+    if (!radius || !offset || (capacity > 0 && (!hit_g || !hit_e || !hit_k || !hit_tof)))
+        return fail(TOFRT_E_BADARG, "tofrt_hits_host: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t E = c->E, g = (size_t)G, S = (size_t)c->n_shooters;
+    // geometries per pass: the dense intermediate stays below ~6 GB
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(g, ((size_t)6 << 30) / (E * 12 * S)));
+    const size_t rows_max = chunk * S;
+    int slot = 0;
+    auto cleanup = [&]() {};  // the workspace is cached in the context
+    auto dalloc = [&](void **q, size_t bytes) {
+        bytes = std::max<size_t>(bytes, 16);
+        const int i = slot++;
+        cudaError_t e = cudaSuccess;
+        if (c->hw_bytes[i] < bytes) {
+            cudaFree(c->hw[i]); c->hw[i] = nullptr; c->hw_bytes[i] = 0;
+            e = cudaMalloc(&c->hw[i], bytes);
+            if (e == cudaSuccess) c->hw_bytes[i] = bytes;
+        }
+        *q = c->hw[i];
+        return e;
+    };
+#define TRY_H(expr)                                                                                    \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) { cleanup(); return fail(TOFRT_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); } \
+    } while (0)
+    double *d_in = nullptr, *d_tof = nullptr, *d_ht = nullptr;
+    int *d_kh = nullptr, *d_hg = nullptr, *d_he = nullptr, *d_hk = nullptr;
+    long long *d_cnt = nullptr, *d_off = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    if (rows_max + 1 > 0x7fffffff) return fail(TOFRT_E_TOOLARGE, "tofrt_hits_host: too many rows per pass");
+    TRY_H(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, d_off, (int)(rows_max + 1)));
+    TRY_H(dalloc((void **)&d_in, sizeof(double) * 2 * g));
+    TRY_H(dalloc((void **)&d_tof, sizeof(double) * rows_max * E));
+    TRY_H(dalloc((void **)&d_kh, sizeof(int) * rows_max * E));
+    TRY_H(dalloc((void **)&d_cnt, sizeof(long long) * (rows_max + 1)));
+    TRY_H(dalloc((void **)&d_off, sizeof(long long) * (rows_max + 1)));
+    TRY_H(dalloc(&d_tmp, tmp_bytes));
+    TRY_H(dalloc((void **)&d_hg, sizeof(int) * (size_t)capacity));
+    TRY_H(dalloc((void **)&d_he, sizeof(int) * (size_t)capacity));
+    TRY_H(dalloc((void **)&d_hk, sizeof(int) * (size_t)capacity));
+    TRY_H(dalloc((void **)&d_ht, sizeof(double) * (size_t)capacity));
+    TRY_H(cudaMemcpy(d_in, radius, sizeof(double) * g, cudaMemcpyHostToDevice));
+    TRY_H(cudaMemcpy(d_in + g, offset, sizeof(double) * g, cudaMemcpyHostToDevice));
+    long long total = 0;
+    if (S > 1 && chunk < g) { cleanup(); return fail(TOFRT_E_TOOLARGE, "tofrt_hits_host: too many geometries x shooters for one pass"); }
+    for (size_t done = 0; done < g; done += chunk) {
+        const size_t n = std::min(chunk, g - done), rows = n * S;
+        int rc = tofrt_table_dev(c, d_in + done, d_in + g + done, (long long)n, d_tof, d_kh, nullptr, nullptr);
+        if (rc != TOFRT_OK) { cleanup(); return rc; }
+        const int blocks = (int)((rows * 32 + 255) / 256);
+        TRY_H(cudaMemsetAsync(d_cnt + rows, 0, sizeof(long long)));
+        tofrt_count_hits_kernel<<<blocks, 256>>>(d_kh, (long long)rows, (int)E, d_cnt);
+        TRY_H(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_cnt, d_off, (int)rows + 1));
+        tofrt_compact_hits_kernel<<<blocks, 256>>>(d_kh, d_tof, (long long)rows, (int)E, d_off, (long long)(done * 1),
+                                                   total, capacity, d_hg, d_he, d_hk, d_ht);
+        TRY_H(cudaGetLastError());
+        long long got = 0;
+        TRY_H(cudaMemcpy(&got, d_off + rows, sizeof(long long), cudaMemcpyDeviceToHost));
+        total += got;
+    }
+    *n_hits = total;
+    const size_t ncopy = (size_t)std::min<long long>(total, capacity);
+    if (ncopy) {
+        TRY_H(cudaMemcpy(hit_g, d_hg, sizeof(int) * ncopy, cudaMemcpyDeviceToHost));
+        TRY_H(cudaMemcpy(hit_e, d_he, sizeof(int) * ncopy, cudaMemcpyDeviceToHost));
+        TRY_H(cudaMemcpy(hit_k, d_hk, sizeof(int) * ncopy, cudaMemcpyDeviceToHost));
+        TRY_H(cudaMemcpy(hit_tof, d_ht, sizeof(double) * ncopy, cudaMemcpyDeviceToHost));
+    }
+    cleanup();
+#undef TRY_H
+    if (total > capacity) return fail(TOFRT_E_TOOLARGE, "tofrt_hits_host: capacity too small (n_hits holds the required size)");
     return TOFRT_OK;
 }
 

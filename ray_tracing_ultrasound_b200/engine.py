@@ -138,6 +138,30 @@ class TofEngine:
                                                ctypes.byref(rec) if rec is not None else None))
         return TofTable(tof, k_hit, out)
 
+    # ---- sparse form: only the hits, ordered by (row, receiver) ---------------------------
+    def tof_hits(self, radii, offsets, capacity=None, buffers=None):
+        """(row, e, k, tof) arrays of the table entries with a hit; row = geometry index
+        (shooter * G + geometry with several shooters).  `buffers` = preallocated (pinned) arrays."""
+        radii, offsets = _f64(radii).ravel(), _f64(offsets).ravel()
+        if radii.shape != offsets.shape:
+            raise ValueError("radii and offsets must have the same length")
+        G = len(radii)
+        n = ctypes.c_longlong(0)
+        while True:
+            if buffers is None:
+                cap = int(capacity) if capacity else max(1024, G * self.S * self.E // 16)
+                bufs = (np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap))
+            else:
+                bufs, cap = buffers, len(buffers[0])
+            rc = self._lib.tofrt_hits_host(self._ctx, radii.ctypes.data, offsets.ctypes.data, G, cap,
+                                           bufs[0].ctypes.data, bufs[1].ctypes.data, bufs[2].ctypes.data,
+                                           bufs[3].ctypes.data, ctypes.byref(n))
+            if rc == _capi.E_TOOLARGE and n.value > cap and buffers is None:
+                capacity = n.value  # retry once with the exact size
+                continue
+            _capi.check(rc)
+            return tuple(b[: n.value] for b in bufs)
+
     # ---- same, device-resident torch tensors, async on the current stream -------
     def tof_table_cuda(self, radii, offsets, out_tof=None, out_k_hit=None, records=()):
         import torch

@@ -378,3 +378,27 @@ def test_many_receivers(engine, oracle_dm, n_elements):
     if n_elements >= 4096:
         with pytest.raises(TofrtError):
             engine.tof_table_f32_cuda(torch.from_numpy(radii).cuda(), torch.from_numpy(offsets).cuda())
+
+
+def test_sparse_hit_list_equals_dense_table(engine):
+    """tofrt_hits_host returns exactly the dense table's hits, ordered by (geometry, receiver)."""
+    x_a, z_a, alpha, zf = _std(engine)
+    radii, offsets = rs.synthetic_grid(60, 50)
+    t = engine.tof_table(radii, offsets)
+    g, e, k, tof = engine.tof_hits(radii, offsets)
+    gg, ee = np.nonzero(t.hit)                     # row-major order = (geometry, receiver)
+    assert len(g) == len(gg) > 1000
+    assert np.array_equal(g, gg) and np.array_equal(e, ee)
+    assert np.array_equal(k, t.k_hit[gg, ee]) and np.array_equal(tof, t.tof[gg, ee])
+    # capacity too small: first `capacity` hits, total reported, then an exact-size retry inside tof_hits
+    g2, e2, k2, tof2 = engine.tof_hits(radii, offsets, capacity=100)
+    assert np.array_equal(g2, gg) and np.array_equal(tof2, tof)
+    # several shooters: row = shooter * G + geometry
+    engine.setup(alpha, zf, x_a[30:34], z_a[30:34], x_a)
+    t4 = engine.tof_table(radii[:200], offsets[:200])
+    g4, e4, k4, tof4 = engine.tof_hits(radii[:200], offsets[:200])
+    ss, gg4, ee4 = np.nonzero(t4.hit)
+    assert np.array_equal(g4, ss * 200 + gg4) and np.array_equal(e4, ee4)
+    assert np.array_equal(tof4, t4.tof[ss, gg4, ee4])
+    # no geometry at all
+    assert all(len(a) == 0 for a in engine.tof_hits([], []))
