@@ -33,15 +33,26 @@ def is_stale():
 
 
 def build(force=False, verbose=False, defines=(), out=None):
-    """Compile csrc/*.cu -> libtofrt.so.  Cross-compiles without a GPU."""
+    """Compile csrc/*.cu -> libtofrt.so.  Cross-compiles without a GPU.  Safe to call from several
+    processes at once (torchrun ranks): an exclusive file lock serialises the compile."""
+    import fcntl
     out = out or LIB_PATH
     if not force and out == LIB_PATH and not is_stale():
         return LIB_PATH
-    cmd = ([nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
-           + ["-o", out] + SOURCES)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    with open(out + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and out == LIB_PATH and not is_stale():
+                return LIB_PATH  # another process built it while we waited
+            tmp = out + f".tmp{os.getpid()}"
+            cmd = ([nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+                   + ["-o", tmp] + SOURCES)
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, out)  # atomic: a reader never sees a half-written library
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return out
