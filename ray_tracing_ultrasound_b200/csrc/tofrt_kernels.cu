@@ -54,6 +54,9 @@ constexpr int kThreads = TOFRT_THREADS;  // warps per CTA = kThreads / 32
 constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 16;            // lens samples per early-exit check
 constexpr int kNoHit = 0x7fffffff;
+#ifndef TOFRT_CHUNK_MB
+#define TOFRT_CHUNK_MB 64  // output bytes per pipelined chunk of tofrt_table_host
+#endif
 
 // Everything the kernels need that does not depend on the geometry.
 struct DevSetup {
@@ -1332,7 +1335,7 @@ int tofrt_table_f32_dev(tofrt_ctx *c, const double *d_radius, const double *d_of
     return TOFRT_OK;
 }
 
-// Host-buffer path: the geometries are cut into chunks whose outputs are ~128 MB; chunk i is
+// Host-buffer path: the geometries are cut into chunks whose outputs are ~64 MB; chunk i is
 // traced on one stream into one of two device slots while the results of chunk i-1 travel to the
 // host on a second stream (pinned host buffers make that copy truly asynchronous), so the
 // end-to-end time is max(compute, PCIe) instead of their sum.  The workspace is owned by the
@@ -1353,7 +1356,7 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
     const int n_rec_d = (R.pipe_x != nullptr) + (R.pipe_z != nullptr) + (R.lens2_x != nullptr) +
                         (R.lens2_z != nullptr) + (R.target_x != nullptr) + 4 * (R.legs != nullptr);
     per_geom += (size_t)n_rec_d * K * sizeof(double) + (R.idx ? K * sizeof(int) : 0);
-    size_t chunk = std::max<size_t>(1, ((size_t)128 << 20) / per_geom);
+    size_t chunk = std::max<size_t>(1, ((size_t)TOFRT_CHUNK_MB << 20) / per_geom);
     chunk = std::min(chunk, g);
     if (g > chunk) {  // even chunks, each a multiple of 1024 geometries
         size_t n = (g + chunk - 1) / chunk;
