@@ -226,7 +226,9 @@ __device__ __forceinline__ void chord_intersection(const double2 *lens, const do
 
 // ---- the table kernel -----------------------------------------------------------
 // HG: first-hit state in the output rows (global memory) instead of warp-private shared memory
-template <bool HG>
+// GUIDED: compile the guided search (its rare fallback is then a plain per-ray exact scan) or the
+// warp-wide literal scan -- two lean instruction streams instead of one kernel carrying both.
+template <bool HG, bool GUIDED>
 __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel(DevSetup S, TableArgs T)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
             int idx = -1;             // >= 0 segment, -1 none
             bool need_scan = fast;    // lanes whose index the O(N) scan below still has to find
             bool skip_on_sample = false;
-            if (S.guided && S.shape != 0) {
+            if (GUIDED) {
                 // ---- guided search: same idx as the scan, in O(log N) diffs ------------------
                 // g_j = shape * diff_j is, in exact arithmetic, a concave sequence over the sampled
                 // lens (chord slopes strictly monotone, checked by tofrt_setup), and a computed diff
@@ -368,7 +370,11 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
             int flagged = -1;
             unsigned gmin = 0xffffffffu;  // min over all chunks of the high words (see below)
             st_rays += valid; st_scan_rays += need_scan;
-            if (__any_sync(FULL, need_scan)) {
+            if (GUIDED) {
+                // a ray the guided search could not decide (|diff| <= tol where it matters): plain exact scan
+                if (__any_sync(FULL, need_scan)) st_scan_warps += (lane == 0);
+                if (need_scan) { idx = scan_exact_from(s_lens, N, m, b, 0); flagged = 0; }
+            } else if (__any_sync(FULL, need_scan)) {
                 st_scan_warps += (lane == 0);
                 unsigned hp = hi32(line_diff(s_lens[0], m, b));
                 for (int base = 1; base < Npad; base += kChunk) {
@@ -388,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                     if (__all_sync(FULL, flagged >= 0 || !need_scan)) break;
                 }
             }
-            if (need_scan && flagged >= 0) {
+            if (!GUIDED && need_scan && flagged >= 0) {
                 // resolve the exact index inside the flagged chunk without a data-dependent loop:
                 // classes (-1, 0, +1) of samples flagged-1 .. flagged+kChunk-1 (all finite here),
                 // bit u of `chg` = class changes between samples j0+u and j0+u+1
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
             if (valid && idx < 0) {
                 if (!fast) idx = scan_exact_from(s_lens, N, m, b, 0);
                 // conservative flag without a real change (a denormal diff): keep going exactly
-                else if (need_scan && flagged >= 0 && flagged + kChunk - 1 < N - 1)
+                else if (!GUIDED && need_scan && flagged >= 0 && flagged + kChunk - 1 < N - 1)
                     idx = scan_exact_from(s_lens, N, m, b, flagged + kChunk - 1);
             }
             // ---- main_rt.py:84-96 no crossing: is a sample on the line (|diff| <= 1e-8)? ----
@@ -1229,13 +1235,16 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
         CUDA_TRY(cudaDeviceSynchronize());
     }
 
-    if (S.hits_in_global)
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (S.hits_in_global) {
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     int occ = 1;
-    if (S.hits_in_global) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<true>, kThreads, smem));
-    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<false>, kThreads, smem));
+    if (S.hits_in_global) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<true, true>, kThreads, smem));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<false, true>, kThreads, smem));
     c->ctas_per_sm = std::max(1, occ);
     c->S = S; c->K = K; c->E = E; c->smem = smem; c->n_shooters = NS; c->params_d = p->d;
     c->ready = true;
@@ -1302,8 +1311,14 @@ static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_
     CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
     long long warps_needed = G * s_count;
     int grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, (warps_needed + kWarps - 1) / kWarps);
-    if (c->S.hits_in_global) tofrt_table_kernel<true><<<grid, kThreads, c->smem, st>>>(c->S, T);
-    else tofrt_table_kernel<false><<<grid, kThreads, c->smem, st>>>(c->S, T);
+    const bool guided = c->S.guided && c->S.shape != 0;
+    if (c->S.hits_in_global) {
+        if (guided) tofrt_table_kernel<true, true><<<grid, kThreads, c->smem, st>>>(c->S, T);
+        else tofrt_table_kernel<true, false><<<grid, kThreads, c->smem, st>>>(c->S, T);
+    } else {
+        if (guided) tofrt_table_kernel<false, true><<<grid, kThreads, c->smem, st>>>(c->S, T);
+        else tofrt_table_kernel<false, false><<<grid, kThreads, c->smem, st>>>(c->S, T);
+    }
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
 }
@@ -1614,7 +1629,7 @@ int tofrt_kernel_info(tofrt_ctx *c, int *grid, int *block, int *smem_bytes, int 
 {
     if (!c) return fail(TOFRT_E_BADARG, "tofrt_kernel_info: ctx is NULL");
     cudaFuncAttributes fa{};
-    CUDA_TRY(cudaFuncGetAttributes(&fa, tofrt_table_kernel<false>));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, tofrt_table_kernel<false, true>));
     if (grid) *grid = c->sm_count * c->ctas_per_sm;
     if (block) *block = kThreads;
     if (smem_bytes) *smem_bytes = (int)c->smem;
