@@ -45,7 +45,7 @@
 namespace {
 
 #ifndef TOFRT_THREADS
-#define TOFRT_THREADS 1024
+#define TOFRT_THREADS 896
 #endif
 #ifndef TOFRT_MIN_BLOCKS
 #define TOFRT_MIN_BLOCKS 1

@@ -402,3 +402,22 @@ def test_sparse_hit_list_equals_dense_table(engine):
     assert np.array_equal(tof4, t4.tof[ss, gg4, ee4])
     # no geometry at all
     assert all(len(a) == 0 for a in engine.tof_hits([], []))
+
+
+def test_host_pipeline_many_chunks_with_records(engine):
+    """The host path cuts the geometries into ~64 MB chunks (double-buffered); with per-ray records a
+    chunk is only ~1 600 geometries, so 5 000 geometries exercise several chunks, the slot reuse and
+    a ragged last chunk.  Must equal the single-launch device path byte for byte."""
+    import torch
+    x_a, z_a, alpha, zf = _std(engine)
+    rng = np.random.default_rng(77)
+    G = 5003
+    radii, offsets = rng.uniform(0.01, 0.1, G), rng.uniform(-0.01, 0.01, G)
+    keys = ("idx", "target_x", "legs", "pipe_z")
+    th = engine.tof_table(radii, offsets, records=keys)
+    td = engine.tof_table_cuda(torch.from_numpy(radii).cuda(), torch.from_numpy(offsets).cuda(), records=keys)
+    torch.cuda.synchronize()
+    assert np.array_equal(th.tof, td.tof.cpu().numpy()) and np.array_equal(th.k_hit, td.k_hit.cpu().numpy())
+    for k in keys:
+        assert _same(th.records[k], td.records[k].cpu().numpy()), k
+    assert th.records["legs"].shape == (G, 4, 905)
