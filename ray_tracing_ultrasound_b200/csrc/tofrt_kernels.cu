@@ -582,6 +582,62 @@ __global__ void tofrt_to_float_kernel(int n, const double *src, float *dst)
 
 #define HALF_PI_F 1.57079632679489661923f
 
+// float elementary functions of the FP32 mode: straight-line, ~1 ulp polynomials (Cephes
+// single-precision coefficients), MUFU-based division / square root.  No parity claim here.
+__device__ __forceinline__ float fsqrt_fast(float x)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ int sincos_reduced_f(float x, float *s, float *c)
+{
+    const float t = fmaf(x, 0.63661975f, 12582912.0f);  // 1.5 * 2^23: round to nearest integer
+    const float n = t - 12582912.0f;
+    const float r = fmaf(-n, -4.371139e-08f, fmaf(-n, 1.5707964f, x));
+    const float z = r * r;
+    *s = fmaf(r * z, fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), r);
+    *c = fmaf(z * z, fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f),
+              fmaf(-0.5f, z, 1.0f));
+    return __float_as_int(t) & 3;
+}
+__device__ __forceinline__ void sincos_f(float x, float *sn, float *cs)
+{
+    float s, c;
+    const int q = sincos_reduced_f(x, &s, &c);
+    float vs = (q & 1) ? c : s, vc = (q & 1) ? s : c;
+    vs = (q & 2) ? -vs : vs;
+    vc = ((q + 1) & 2) ? -vc : vc;
+    const bool ok = fabsf(x) < 1.0e6f;
+    *sn = ok ? vs : NAN;
+    *cs = ok ? vc : NAN;
+}
+__device__ __forceinline__ float tan_f(float x)
+{
+    float s, c;
+    const int q = sincos_reduced_f(x, &s, &c);
+    const float v = (q & 1) ? __fdividef(-c, s) : __fdividef(s, c);
+    return fabsf(x) < 1.0e6f ? v : NAN;
+}
+__device__ __forceinline__ float atan2_f(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const bool swap = ay > ax;
+    const float a = swap ? ax : ay, b = swap ? ay : ax;
+    const bool small = a < 0.41421356f * b;  // tan(pi/8)
+    const float u = __fdividef(small ? a : a - b, small ? b : a + b);
+    const float z = u * u;
+    float r = fmaf(u * z, fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z,
+                               -3.33329491539e-1f), u);
+    r = small ? r : r + 0.78539816339744830962f;
+    r = (b == 0.0f) ? 0.0f : r;
+    r = (a == INFINITY && b == INFINITY) ? 0.78539816339744830962f : r;
+    r = swap ? 1.57079632679489661923f - r : r;
+    r = signbit(x) ? 3.14159265358979323846f - r : r;
+    return copysignf(r, y);
+}
+__device__ __forceinline__ float asin_f(float x) { return atan2_f(x, fsqrt_fast((1.0f - x) * (1.0f + x))); }
+
 __device__ __forceinline__ float line_diff_f(float2 s, float m, float b) { return s.y - (m * s.x + b); }
 __device__ __forceinline__ int sign_class_f(float v) { return v > 0 ? 2 : (v < 0 ? 0 : (v == 0 ? 1 : 3)); }
 __device__ __forceinline__ bool np_isclose_f(float a, float b, float rtol, float atol)
@@ -646,9 +702,9 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
                 float A2 = a_pq * a_pq + 1;
                 float B2 = 2 * (a_pq * b_pq - pipe_offset);
                 float C2 = offsq + b_pq * b_pq - rsq;
-                float sd = sqrtf(B2 * B2 - 4 * A2 * C2);
+                float sd = fsqrt_fast(B2 * B2 - 4 * A2 * C2);
                 float den = 2 * A2;
-                float x_q1 = (-B2 + sd) / den, x_q2 = (-B2 - sd) / den;
+                float x_q1 = __fdividef(-B2 + sd, den), x_q2 = __fdividef(-B2 - sd, den);
                 float z_q1 = a_pq * x_q1 + b_pq, z_q2 = a_pq * x_q2 + b_pq;
                 bool up = z_q1 > z_q2;
                 x_q = up ? x_q1 : x_q2;
@@ -656,11 +712,11 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
             }
             float phi_l, m, b;
             {
-                float slope = -x_q / sqrtf(rsq - x_q * x_q);
-                float phi_slope = atanf(slope);
+                float slope = __fdividef(-x_q, fsqrt_fast(rsq - x_q * x_q));
+                float phi_slope = atan2_f(slope, 1.0f);
                 float theta_1 = phi_pq - (phi_slope + HALF_PI_F);
                 phi_l = phi_slope - HALF_PI_F + (-theta_1);
-                m = tanf(phi_l);
+                m = tan_f(phi_l);
                 b = z_q - m * x_q;
             }
             const bool fin = valid && fabsf(m) < 1e18f && fabsf(b) < 1e18f;
@@ -716,7 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
                 } else if (np_isclose_f(m, sg.x, 1e-5f, 1e-8f)) {
                     if (np_isclose_f(b, sg.y, 1e-5f, 1e-8f)) { ix = (p1.x + p2.x) / 2.0f; iz = m * ix + b; }
                 } else {
-                    float x_int = (sg.y - b) / (m - sg.x), y_int = m * x_int + b;
+                    float x_int = __fdividef(sg.y - b, m - sg.x), y_int = m * x_int + b;
                     if (x_int >= fminf(p1.x, p2.x) - 1e-9f && x_int <= fmaxf(p1.x, p2.x) + 1e-9f &&
                         y_int >= fminf(p1.y, p2.y) - 1e-9f && y_int <= fmaxf(p1.y, p2.y) + 1e-9f) { ix = x_int; iz = y_int; }
                 }
@@ -726,25 +782,27 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
             }
             float target_x = NAN;
             if (__any_sync(FULL, valid && ix == ix)) {
-                float alpha_i = atan2f(ix, iz);
+                float alpha_i = atan2_f(ix, iz);
                 float sn, cs;
-                sincosf(alpha_i, &sn, &cs);
+                sincos_f(alpha_i, &sn, &cs);
                 float B = S.twod * cs - S.K2;
-                float sd = sqrtf(B * B - S.fourAC);
-                float hh = (-B - sd) / S.twoA;
+                float sd = fsqrt_fast(B * B - S.fourAC);
+                float hh = __fdividef(-B - sd, S.twoA);
                 float dB = -S.twod * sn;
-                float dS = (1 / (2 * sd)) * (2 * B * dB);
+                float dS = __fdividef(1.0f, 2 * sd) * (2 * B * dB);
                 float dh = S.phi1 * (dB + dS);
                 float dz = dh * cs - hh * sn, dx = dh * sn + hh * cs;
-                float phi_slope = atan2f(dz, dx);
+                float phi_slope = atan2_f(dz, dx);
                 float theta_1 = phi_l - (phi_slope + HALF_PI_F);
-                float s_arg = S.c1_over_c2 * sinf(theta_1);
+                float sn1, cs1;
+                sincos_f(theta_1, &sn1, &cs1);
+                float s_arg = S.c1_over_c2 * sn1;
                 if (__any_sync(FULL, valid && fabsf(s_arg) <= 1.0f)) {
-                    float theta_2 = asinf(s_arg);
+                    float theta_2 = asin_f(s_arg);
                     float phi_last = phi_slope - HALF_PI_F + theta_2;
-                    float a_i = tanf(phi_last);
+                    float a_i = tan_f(phi_last);
                     float b_i = iz - a_i * ix;
-                    target_x = (z_f - b_i) / a_i;
+                    target_x = __fdividef(z_f - b_i, a_i);
                 }
             }
             bool cand = valid && target_x >= S.rx_min - S.tol_max && target_x <= S.rx_max + S.tol_max;
