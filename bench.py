@@ -54,6 +54,20 @@ def workload(rank, world, grid_r=GRID_R, grid_o=GRID_O):
     return x_a, z_a, alpha, zf, radii[sl], offsets[sl]
 
 
+def e2e_block(E, G, world, dense_value, steps, dense_ok, hits_value, nh, hits_ok):
+    """End-to-end numbers through the C ABI with host buffers.  Both forms deliver the complete result
+    of the step to the host: the dense table (tofrt_table_host) or the list of its hits
+    (tofrt_hits_host; every other entry is `False, 0`).  `value` is the better of the two."""
+    dense = {"value": dense_value, "unit": UNIT, "h2d_bytes_per_step": int(G * 16 * world),
+             "d2h_bytes_per_step": int(G * E * 12 * world), "matches_device_path": dense_ok}
+    sparse = {"value": hits_value, "unit": UNIT, "h2d_bytes_per_step": int(G * 16 * world),
+              "d2h_bytes_per_step": int(nh * 20 * world), "hits_per_step": nh * world, "matches_dense": hits_ok}
+    best, form = (sparse, "sparse_hits") if hits_value > dense_value and hits_ok else (dense, "dense")
+    return {"value": best["value"], "unit": UNIT, "form": form, "h2d_bytes_per_step": best["h2d_bytes_per_step"],
+            "d2h_bytes_per_step": best["d2h_bytes_per_step"], "steps": steps, "dense": dense, "sparse_hits": sparse,
+            "note": "pinned host buffers; H2D of radius/offset and D2H of the result inside the timed region"}
+
+
 def algorithmic_ops(G, K, N, E):
     """W_g = K*(155 + 3N) + 2*E*K FP64 ops per geometry."""
     return float(G) * (K * (155.0 + 3.0 * N) + 2.0 * E * K)
@@ -368,13 +382,7 @@ def main():
                        "l2": "outputs (1.6 GB per step) exceed L2; inputs are 16 MB + 60 KB of tables",
                        "kernel": info},
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(G * 16 * world),
-                    "d2h_bytes_per_step": int(G * E * 12 * world), "steps": e2e_steps,
-                    "matches_device_path": parity_ok,
-                    "sparse_hits": {"value": hits_value, "unit": UNIT, "d2h_bytes_per_step": int(nh * 20 * world),
-                                    "hits_per_step": nh * world, "matches_dense": hits_ok,
-                                    "note": "same pass through tofrt_hits_host: the host receives only the "
-                                            "(row, receiver, ray, tof) list of the hits (2 % of the entries)"}},
+            "e2e": e2e_block(E, G, world, e2e_value, e2e_steps, parity_ok, hits_value, nh, hits_ok),
             "gpu_launches": args.steps * 1,
             "roofline": roofline,
         }
