@@ -152,6 +152,11 @@ int tofrt_fermat_dev(tofrt_ctx *ctx, const double *d_fx, const double *d_fz, lon
 int tofrt_fermat_host(tofrt_ctx *ctx, const double *fx, const double *fz, long long F, double *tof,
                       int *kmin, double *alpha);
 
+/* Test hook: apply the return-path search of find_line_curve_intersection (main_rt.py:78-99,
+ * current setup, current TOFRT_OPT_SEARCH mode) to n arbitrary lines y = m[i] x + b[i].  Runs the
+ * production kernel with the reflected lines replaced; idx[i] is encoded as in tofrt_ray_records. */
+int tofrt_debug_search_host(tofrt_ctx *ctx, const double *m, const double *b, long long n, int *idx);
+
 /* Roofline denominator, measured on the device the context lives on: FP64
  * instructions per second (thread-level) of a DFMA stream and of the un-fused
  * DMUL+DADD stream the search loop issues (SURVEY.md section 8 d). */

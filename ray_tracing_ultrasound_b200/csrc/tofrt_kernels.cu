@@ -90,6 +90,7 @@ struct TableArgs {
     int *k_hit;
     tofrt_ray_records rec;
     int s_begin, s_count;  // shooters [s_begin, s_begin + s_count) of the setup; outputs are [s_count][G][...]
+    const double *inject_m, *inject_b;  // test hook (tofrt_debug_search_host): replace the reflected line of ray [w][k]
     unsigned long long *counter;
     unsigned long long *stats;  // [4]: rays traced, rays that needed the O(N) scan, warp-chunks that ran it, on-sample passes
 };
@@ -304,6 +305,10 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                 m = tofrt_tan(phi_l);
                 b = z_q - m * x_q;
             }
+            if (T.inject_m) {  // test hook: search an arbitrary line instead (uniform branch, off in production)
+                m = T.inject_m[(size_t)w * K + kk];
+                b = T.inject_b[(size_t)w * K + kk];
+            }
 
             // ---- main_rt.py:78-99 first sign change over the sampled lens ----
             // fast path precondition: every diff is finite, so only {-,0,+} occur
@@ -348,8 +353,11 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                     // hi = lo + 1 failed the test (or is the untested last sample).  If g_hi is still
                     // certainly negative, hi is at/after the maximum while lo is before it: g_hi IS
                     // the maximum of g, so no diff is >= 0.
+                    // (lo == 0 was never tested against the slope: if g already falls from the first
+                    // sample on, the maximum is g_0 -- so the bound below uses the larger of the two)
                     const double ghi = sh * line_diff(s_lens[hi], m, b);
-                    if (ghi < -tol) { bracket = false; certain_none = true; edge = -ghi - tol; }
+                    const double glo = sh * line_diff(s_lens[lo], m, b);
+                    if (ghi < -tol) { bracket = false; certain_none = true; edge = -fmax(ghi, glo) - tol; }
                 }
                 if (bracket) {
                     // exact classes from lo on (normally one step)
@@ -742,8 +750,8 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
                     hi = (act && !cond) ? mid : hi;
                 }
                 if (bracket && neg0) {
-                    const float ghi = sh * line_diff_f(s_lens[hi], m, b);
-                    if (ghi < -tol) { bracket = false; none = true; edge = -ghi - tol; }
+                    const float ghi = sh * line_diff_f(s_lens[hi], m, b), glo = sh * line_diff_f(s_lens[lo], m, b);
+                    if (ghi < -tol) { bracket = false; none = true; edge = -fmaxf(ghi, glo) - tol; }
                 }
                 if (bracket) {
                     int cprev = sign_class_f(line_diff_f(s_lens[lo], m, b));
@@ -1352,7 +1360,8 @@ int tofrt_lens_host(tofrt_ctx *c, double *lens_x, double *lens_z)
 }
 
 static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_offset, long long G, double *d_tof,
-                          int *d_k_hit, const tofrt_ray_records *d_rec, void *stream, int s_begin, int s_count)
+                          int *d_k_hit, const tofrt_ray_records *d_rec, void *stream, int s_begin, int s_count,
+                          const double *inject_m = nullptr, const double *inject_b = nullptr)
 {
     if (!c || G < 0) return fail(TOFRT_E_BADARG, "tofrt_table_dev: bad argument");
     if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_table_dev: call tofrt_setup first");
@@ -1364,6 +1373,7 @@ static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_
     T.radius = d_radius; T.offset = d_offset; T.G = G; T.tof = d_tof; T.k_hit = d_k_hit;
     if (d_rec) T.rec = *d_rec;
     T.s_begin = s_begin; T.s_count = s_count;
+    T.inject_m = inject_m; T.inject_b = inject_b;
     T.counter = c->d_counter;
     T.stats = c->d_counter + 1;
     CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
@@ -1506,6 +1516,46 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
     if (rc != TOFRT_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess)
         return fail(TOFRT_E_CUDA, std::string("tofrt_table_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return TOFRT_OK;
+}
+
+// Test hook: the return-path search of the current setup applied to arbitrary lines (m[i], b[i]).
+// It runs the production table kernel with the reflected lines replaced, so it exercises exactly
+// the code the engine ships (both search modes); idx[i] uses the encoding of tofrt_ray_records.
+int tofrt_debug_search_host(tofrt_ctx *c, const double *m, const double *b, long long n, int *idx)
+{
+    if (!c || n < 0) return fail(TOFRT_E_BADARG, "tofrt_debug_search_host: bad argument");
+    if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_debug_search_host: call tofrt_setup first");
+    if (n == 0) return TOFRT_OK;
+    if (!m || !b || !idx) return fail(TOFRT_E_BADARG, "tofrt_debug_search_host: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t K = c->K, E = c->E, G = ((size_t)n + K - 1) / K, tot = G * K;
+    std::vector<double> hm(tot, 0.0), hb(tot, 0.0), geo(2 * G);
+    std::copy(m, m + n, hm.begin());
+    std::copy(b, b + n, hb.begin());
+    for (size_t g = 0; g < G; ++g) { geo[g] = 0.05; geo[G + g] = 0.0; }
+    double *d_m = nullptr, *d_geo = nullptr, *d_tof = nullptr;
+    int *d_kh = nullptr, *d_idx = nullptr;
+    cudaError_t e = cudaMalloc(&d_m, sizeof(double) * 2 * tot);
+    if (e == cudaSuccess) e = cudaMalloc(&d_geo, sizeof(double) * 2 * G);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tof, sizeof(double) * G * E);
+    if (e == cudaSuccess) e = cudaMalloc(&d_kh, sizeof(int) * G * E);
+    if (e == cudaSuccess) e = cudaMalloc(&d_idx, sizeof(int) * tot);
+    if (e == cudaSuccess) e = cudaMemcpy(d_m, hm.data(), sizeof(double) * tot, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_m + tot, hb.data(), sizeof(double) * tot, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_geo, geo.data(), sizeof(double) * 2 * G, cudaMemcpyHostToDevice);
+    int rc = TOFRT_OK;
+    if (e == cudaSuccess) {
+        tofrt_ray_records rec{};
+        rec.idx = d_idx;
+        rc = table_dev_impl(c, d_geo, d_geo + G, (long long)G, d_tof, d_kh, &rec, nullptr, 0, 1, d_m, d_m + tot);
+    }
+    std::vector<int> hidx(tot);
+    if (e == cudaSuccess && rc == TOFRT_OK) e = cudaMemcpy(hidx.data(), d_idx, sizeof(int) * tot, cudaMemcpyDeviceToHost);
+    cudaFree(d_m); cudaFree(d_geo); cudaFree(d_tof); cudaFree(d_kh); cudaFree(d_idx);
+    if (rc != TOFRT_OK) return rc;
+    if (e != cudaSuccess) return fail(TOFRT_E_CUDA, std::string("tofrt_debug_search_host: ") + cudaGetErrorString(e));
+    std::copy(hidx.begin(), hidx.begin() + n, idx);
     return TOFRT_OK;
 }
 
