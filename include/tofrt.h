@@ -154,8 +154,10 @@ int tofrt_fermat_host(tofrt_ctx *ctx, const double *fx, const double *fz, long l
 
 /* Test hook: apply the return-path search of find_line_curve_intersection (main_rt.py:78-99,
  * current setup, current TOFRT_OPT_SEARCH mode) to n arbitrary lines y = m[i] x + b[i].  Runs the
- * production kernel with the reflected lines replaced; idx[i] is encoded as in tofrt_ray_records. */
-int tofrt_debug_search_host(tofrt_ctx *ctx, const double *m, const double *b, long long n, int *idx);
+ * production kernel with the reflected lines replaced; idx[i] is encoded as in tofrt_ray_records;
+ * xi/zi (nullable) receive the intersection point of main_rt.py:106-168 (NaN = None). */
+int tofrt_debug_search_host(tofrt_ctx *ctx, const double *m, const double *b, long long n, int *idx,
+                            double *xi, double *zi);
 
 /* Roofline denominator, measured on the device the context lives on: FP64
  * instructions per second (thread-level) of a DFMA stream and of the un-fused

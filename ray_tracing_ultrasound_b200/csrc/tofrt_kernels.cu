@@ -1522,7 +1522,8 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
 // Test hook: the return-path search of the current setup applied to arbitrary lines (m[i], b[i]).
 // It runs the production table kernel with the reflected lines replaced, so it exercises exactly
 // the code the engine ships (both search modes); idx[i] uses the encoding of tofrt_ray_records.
-int tofrt_debug_search_host(tofrt_ctx *c, const double *m, const double *b, long long n, int *idx)
+int tofrt_debug_search_host(tofrt_ctx *c, const double *m, const double *b, long long n, int *idx, double *xi,
+                            double *zi)
 {
     if (!c || n < 0) return fail(TOFRT_E_BADARG, "tofrt_debug_search_host: bad argument");
     if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_debug_search_host: call tofrt_setup first");
@@ -1536,7 +1537,9 @@ int tofrt_debug_search_host(tofrt_ctx *c, const double *m, const double *b, long
     for (size_t g = 0; g < G; ++g) { geo[g] = 0.05; geo[G + g] = 0.0; }
     double *d_m = nullptr, *d_geo = nullptr, *d_tof = nullptr;
     int *d_kh = nullptr, *d_idx = nullptr;
+    double *d_xz = nullptr;
     cudaError_t e = cudaMalloc(&d_m, sizeof(double) * 2 * tot);
+    if (e == cudaSuccess) e = cudaMalloc(&d_xz, sizeof(double) * 2 * tot);
     if (e == cudaSuccess) e = cudaMalloc(&d_geo, sizeof(double) * 2 * G);
     if (e == cudaSuccess) e = cudaMalloc(&d_tof, sizeof(double) * G * E);
     if (e == cudaSuccess) e = cudaMalloc(&d_kh, sizeof(int) * G * E);
@@ -1548,10 +1551,14 @@ int tofrt_debug_search_host(tofrt_ctx *c, const double *m, const double *b, long
     if (e == cudaSuccess) {
         tofrt_ray_records rec{};
         rec.idx = d_idx;
+        rec.lens2_x = d_xz; rec.lens2_z = d_xz + tot;
         rc = table_dev_impl(c, d_geo, d_geo + G, (long long)G, d_tof, d_kh, &rec, nullptr, 0, 1, d_m, d_m + tot);
     }
     std::vector<int> hidx(tot);
     if (e == cudaSuccess && rc == TOFRT_OK) e = cudaMemcpy(hidx.data(), d_idx, sizeof(int) * tot, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == TOFRT_OK && xi) e = cudaMemcpy(xi, d_xz, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && rc == TOFRT_OK && zi) e = cudaMemcpy(zi, d_xz + tot, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    cudaFree(d_xz);
     cudaFree(d_m); cudaFree(d_geo); cudaFree(d_tof); cudaFree(d_kh); cudaFree(d_idx);
     if (rc != TOFRT_OK) return rc;
     if (e != cudaSuccess) return fail(TOFRT_E_CUDA, std::string("tofrt_debug_search_host: ") + cudaGetErrorString(e));

@@ -97,12 +97,17 @@ class TofEngine:
         _capi.check(self._lib.tofrt_last_stats(self._ctx, arr))
         return dict(zip(("rays", "scan_rays", "scan_groups", "on_sample_rays"), (int(x) for x in arr)))
 
-    def debug_search(self, m, b):
-        """Test hook: the return-path search (current mode) applied to arbitrary lines y = m x + b."""
+    def debug_search(self, m, b, with_points=False):
+        """Test hook: find_line_curve_intersection of the current setup (current search mode) applied
+        to arbitrary lines y = m x + b -> idx (and the intersection points)."""
         m, b = _f64(m).ravel(), _f64(b).ravel()
         idx = np.empty(len(m), dtype=np.int32)
-        _capi.check(self._lib.tofrt_debug_search_host(self._ctx, m.ctypes.data, b.ctypes.data, len(m), idx.ctypes.data))
-        return idx
+        xi = np.empty(len(m)) if with_points else None
+        zi = np.empty(len(m)) if with_points else None
+        _capi.check(self._lib.tofrt_debug_search_host(self._ctx, m.ctypes.data, b.ctypes.data, len(m), idx.ctypes.data,
+                                                      xi.ctypes.data if with_points else None,
+                                                      zi.ctypes.data if with_points else None))
+        return (idx, xi, zi) if with_points else idx
 
     def lens(self):
         """lens_1_x, lens_1_z (main_rt.py:338)."""

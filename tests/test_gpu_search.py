@@ -25,6 +25,42 @@ def numpy_rule(x, z, m, b):
     return out
 
 
+def numpy_intersection(x_curve, y_curve, m, b):
+    """main_rt.py:78-168 for a non-vertical line given as (m, b): restated in NumPy scalar arithmetic
+    (np.isclose defaults, Python min/max), returning (x, y) or (nan, nan) for (None, None)."""
+    nan = (np.nan, np.nan)
+    with np.errstate(all="ignore"):
+        diffs = y_curve - (m * x_curve + b)
+        sign_changes = np.where(np.diff(np.sign(diffs)) != 0)[0]
+        if len(sign_changes) == 0:
+            on_line = np.isclose(diffs, 0)
+            if np.any(on_line):
+                i = np.where(on_line)[0][0]
+                return x_curve[i], y_curve[i]
+            return nan
+        idx = sign_changes[0]
+        x1, y1 = x_curve[idx], y_curve[idx]
+        x2, y2 = x_curve[idx + 1], y_curve[idx + 1]
+        if np.isclose(x1, x2):
+            y_int = m * x1 + b
+            if y_int >= min(y1, y2) - 1e-9 and y_int <= max(y1, y2) + 1e-9:
+                return x1, y_int
+            return nan
+        m_seg = (y2 - y1) / (x2 - x1)
+        b_seg = y1 - m_seg * x1
+        if np.isclose(m, m_seg):
+            if np.isclose(b, b_seg):
+                x_int = (x1 + x2) / 2.0
+                return x_int, m * x_int + b
+            return nan
+        x_int = (b_seg - b) / (m - m_seg)
+        y_int = m * x_int + b
+        if (x_int >= min(x1, x2) - 1e-9 and x_int <= max(x1, x2) + 1e-9 and
+                y_int >= min(y1, y2) - 1e-9 and y_int <= max(y1, y2) + 1e-9):
+            return x_int, y_int
+        return nan
+
+
 def adversarial_lines(x, z, rng):
     n = len(x)
     seg_m = np.diff(z) / np.diff(x)
@@ -67,9 +103,15 @@ def test_search_matches_numpy_rule_on_adversarial_lines(engine, n_alpha):
     m, b = adversarial_lines(x, z, rng)
     want = numpy_rule(x, z, m, b)
     assert (want >= 0).sum() > 1000 and (want == -1).sum() > 100 and (want < -1).sum() > 20
+    pts = np.array([numpy_intersection(x, z, np.float64(mi), np.float64(bi)) for mi, bi in zip(m, b)])
+    assert np.isnan(pts[:, 0]).sum() > 100 and (~np.isnan(pts[:, 0])).sum() > 1000
     for mode in ("guided", "scan"):
         engine.set_search(mode)
-        got = engine.debug_search(m, b)
+        got, xi, zi = engine.debug_search(m, b, with_points=True)
         bad = np.nonzero(got != want)[0]
         assert len(bad) == 0, (mode, bad[:10], got[bad[:10]], want[bad[:10]], m[bad[:10]], b[bad[:10]])
+        # the intersection point of main_rt.py:106-168 (collinear / parallel / out-of-bounds branches
+        # included), bit for bit
+        assert np.array_equal(xi, pts[:, 0], equal_nan=True), mode
+        assert np.array_equal(zi, pts[:, 1], equal_nan=True), mode
     engine.set_search("guided")
