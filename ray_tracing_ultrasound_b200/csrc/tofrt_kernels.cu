@@ -1,27 +1,29 @@
 // tofrt_kernels.cu -- sm_100a kernels + C ABI of the TOF ray-tracing engine.
 //
 // What is computed is the reference's pulse-echo trace (main_rt.py:337-405) and
-// table assembly (main_rt.py:487-501); how it is computed is B200-first:
+// table assembly (main_rt.py:487-501); how it is computed is B200-first (DESIGN.md):
 //
-//   tofrt_prepare_kernel   geometry-independent work, once per setup: lens
-//                          samples, tangents, incident leg, first refraction
-//                          (main_rt.py:338-349) -> small tables in HBM/L2.
-//   tofrt_table_kernel     persistent grid (one CTA per SM).  The tables are
-//                          staged once per CTA in shared memory; every WARP
-//                          owns one geometry at a time (dynamic work counter),
-//                          walks its K rays 32 at a time with all per-ray state
-//                          in registers, and keeps the per-receiver first-hit
-//                          reduction warp-private in shared memory, so the
-//                          steady state has no block-level barrier at all.
-//                          The O(N) first-sign-change search of
-//                          find_line_curve_intersection (main_rt.py:78-99) is
-//                          the hot loop: broadcast LDS.128 of one lens sample,
-//                          DMUL+DADD+DADD (never fused: NumPy rounds twice),
-//                          and a 3-input integer min/max on the high words that
-//                          detects "sign change or exact zero in this chunk";
-//                          the warp leaves the loop when every lane has found
-//                          its chunk, and the exact index is resolved once
-//                          afterwards.
+//   tofrt_prepare_kernel, tofrt_chord_kernel
+//       geometry-independent work, once per setup: lens samples, tangents, chords, incident leg
+//       and first refraction of every shooter (main_rt.py:338-349) -> small tables in HBM/L2.
+//   tofrt_table_kernel<HG, GUIDED>
+//       persistent grid, one CTA per SM.  Lens samples and chords are staged once per CTA in
+//       shared memory; every WARP owns one (shooter, geometry) at a time (dynamic work counter),
+//       walks its K rays 32 at a time with all per-ray state in registers and keeps the
+//       per-receiver first-hit reduction warp-private, so the steady state has no block barrier.
+//       The return-path entry index of find_line_curve_intersection (main_rt.py:78-99) comes from
+//         GUIDED = true   a warp-uniform bisection that brackets the first sign change with every
+//                         earlier sign proved (docs/guided_search.md), O(log N) diffs per ray;
+//         GUIDED = false  the reference's literal O(N) scan: broadcast LDS.128 of one lens sample,
+//                         DMUL+DADD+DADD (never fused: NumPy rounds twice) and a 3-input integer
+//                         min/max on the high words ("sign change or exact zero in this chunk"),
+//                         warp-wide early exit, exact index resolved once afterwards.
+//       Both return identical bits.  HG = true keeps the first-hit state in the output rows
+//       (many receivers).
+//   tofrt_table_kernel_f32      the same pipeline in float (FP32 mode, reported separately).
+//   tofrt_count_hits / tofrt_compact_hits (+ CUB scan)   sparse hit list for the host.
+//   tofrt_fermat_kernel         two-point minimum-time entry point (extension).
+//   tofrt_fp64_peak_kernel      FP64 issue-rate micro-benchmark (the roofline denominator).
 //
 // Compile with -fmad=false: the only fused operations are the explicit fma()
 // calls inside tofrt_math.h (shared bit-for-bit with the oracle's twin build).
