@@ -421,3 +421,31 @@ def test_host_pipeline_many_chunks_with_records(engine):
     for k in keys:
         assert _same(th.records[k], td.records[k].cpu().numpy()), k
     assert th.records["legs"].shape == (G, 4, 905)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_other_material_and_lens_parameters(engine, oracle_dm, seed):
+    """Nothing is specialised to the reference's constants (main_rt.py:449-460): random wave speeds,
+    lens dimensions, apertures, ray counts and tolerances stay bit-identical to the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    kw = dict(c1=rng.uniform(3000, 7000), c2=rng.uniform(900, 2500),
+              l0=rng.uniform(0.05, 0.2), h0=rng.uniform(0.04, 0.12))
+    K = int(rng.integers(100, 1500))
+    n_el = int(rng.choice([16, 32, 96]))
+    d = float(np.float64(kw["l0"]) + np.float64(kw["h0"]))
+    x_a, _ = rs.transducer(num_elements=n_el, pitch=np.float64(rng.uniform(2e-4, 1e-3)), d=d)
+    alpha = np.linspace(-rng.uniform(0.3, 0.8), rng.uniform(0.3, 0.8), K)
+    zf = np.ones(K) * d + rng.uniform(-1e-3, 1e-3, K)          # a ragged focus line: z_f is an array (main_rt.py:404)
+    shooter = int(rng.integers(0, len(x_a)))
+    rtol, atol = 10.0 ** rng.uniform(-7, -4), 10.0 ** rng.uniform(-7, -4)
+    engine.setup(alpha, zf, x_a[shooter], d, x_a, rtol=rtol, atol=atol, **kw)
+    G = 300
+    radii = rng.uniform(0.1, 0.9, G) * kw["h0"]
+    offsets = rng.uniform(-0.15, 0.15, G) * kw["h0"]
+    t = engine.tof_table(radii, offsets, records=("idx", "target_x"))
+    p = oracle_dm.params(**kw)
+    tof, k_hit, idx = oracle_dm.table(p, radii, offsets, x_a[shooter], d, zf, alpha, x_a, rtol=rtol, atol=atol,
+                                      want_idx=True)
+    assert np.array_equal(t.records["idx"], idx)
+    assert np.array_equal(t.k_hit, k_hit.T) and np.array_equal(t.tof, tof.T)
+    assert (idx >= 0).mean() > 0.3
