@@ -23,6 +23,8 @@
 #ifndef TOFRT_H
 #define TOFRT_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -124,6 +126,11 @@ int tofrt_table_dev(tofrt_ctx *ctx, const double *d_radius, const double *d_offs
                     double *d_tof, int *d_k_hit, const tofrt_ray_records *d_rec, void *stream);
 int tofrt_table_host(tofrt_ctx *ctx, const double *radius, const double *offset, long long G,
                      double *tof, int *k_hit, const tofrt_ray_records *rec);
+
+/* Page-locked host memory for the buffers handed to the *_host entry points (optional: any host
+ * pointer works, pinned ones let the result copies overlap the kernels).  NULL on failure. */
+void *tofrt_host_alloc(size_t bytes);
+void tofrt_host_free(void *p);
 
 /* Sparse form of tofrt_table_host: only the hits (k_hit >= 0), ordered by (row, receiver), where
  * row = geometry index (shooter * G + geometry with several shooters).  The dense table is

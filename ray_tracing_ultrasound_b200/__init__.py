@@ -7,6 +7,6 @@ is the host-side mirror of the reference interface.  There is no CPU fallback.
 """
 from . import reference_setup
 from ._capi import TofrtError
-from .engine import TofEngine, TofTable
+from .engine import TofEngine, TofTable, pinned_empty
 
-__all__ = ["TofEngine", "TofTable", "TofrtError", "reference_setup"]
+__all__ = ["TofEngine", "TofTable", "TofrtError", "pinned_empty", "reference_setup"]

@@ -30,7 +30,7 @@ class RayRecords(ctypes.Structure):
 
 
 EXPORTS = ["tofrt_version", "tofrt_last_error", "tofrt_device_count", "tofrt_create", "tofrt_destroy",
-           "tofrt_setup", "tofrt_setup_shooters", "tofrt_set_option", "tofrt_get_info", "tofrt_last_stats", "tofrt_lens_host", "tofrt_table_dev", "tofrt_table_f32_dev", "tofrt_table_host", "tofrt_hits_host", "tofrt_debug_search_host", "tofrt_fermat_dev", "tofrt_fermat_host", "tofrt_kernel_info", "tofrt_measure_fp64_peak"]
+           "tofrt_setup", "tofrt_setup_shooters", "tofrt_set_option", "tofrt_get_info", "tofrt_last_stats", "tofrt_lens_host", "tofrt_table_dev", "tofrt_table_f32_dev", "tofrt_table_host", "tofrt_host_alloc", "tofrt_host_free", "tofrt_hits_host", "tofrt_debug_search_host", "tofrt_fermat_dev", "tofrt_fermat_host", "tofrt_kernel_info", "tofrt_measure_fp64_peak"]
 
 _lib = None
 
@@ -67,6 +67,10 @@ def load():
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.tofrt_table_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(RayRecords)]
+    lib.tofrt_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.tofrt_host_alloc.restype = ctypes.c_void_p
+    lib.tofrt_host_free.argtypes = [ctypes.c_void_p]
+    lib.tofrt_host_free.restype = None
     lib.tofrt_hits_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
                                     ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.POINTER(ctypes.c_longlong)]

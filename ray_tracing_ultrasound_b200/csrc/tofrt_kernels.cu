@@ -1568,6 +1568,24 @@ int tofrt_debug_search_host(tofrt_ctx *c, const double *m, const double *b, long
     return TOFRT_OK;
 }
 
+// Page-locked host memory for the callers of the *_host entry points: with pinned buffers the
+// device->host copies of tofrt_table_host overlap the kernels; with pageable memory they are staged.
+void *tofrt_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        fail(TOFRT_E_CUDA, "tofrt_host_alloc: cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+
+void tofrt_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, long long G, long long capacity,
                     int *hit_g, int *hit_e, int *hit_k, double *hit_tof, long long *n_hits)
 {

@@ -19,6 +19,22 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def pinned_empty(shape, dtype=np.float64):
+    """NumPy array in page-locked host memory (tofrt_host_alloc): pass such arrays as `out=` to
+    TofEngine.tof_table so that the result copies overlap the kernels.  Freed with the array."""
+    import weakref
+    lib = _capi.load()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib.tofrt_host_alloc(max(nbytes, 1))
+    if not ptr:
+        raise MemoryError("tofrt_host_alloc failed")
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.tofrt_host_free, ptr)
+    return arr
+
+
 class TofTable:
     """Element x geometry table, geometry-major: tof[g, e], k_hit[g, e]."""
 
@@ -127,13 +143,21 @@ class TofEngine:
         return a.value, b.value
 
     # ---- main_rt.py:464-501, host buffers -------------------------------------
-    def tof_table(self, radii, offsets, records=()):
+    def tof_table(self, radii, offsets, records=(), out=None):
+        """out = (tof, k_hit): preallocated C-contiguous arrays (float64 / int32), e.g. from
+        `pinned_empty`, reused across calls."""
         radii, offsets = _f64(radii).ravel(), _f64(offsets).ravel()
         if radii.shape != offsets.shape:
             raise ValueError("radii and offsets must have the same length")
         G = len(radii)
-        tof = np.empty(self._shape(G, self.E))
-        k_hit = np.empty(self._shape(G, self.E), dtype=np.int32)
+        if out is None:
+            tof = np.empty(self._shape(G, self.E))
+            k_hit = np.empty(self._shape(G, self.E), dtype=np.int32)
+        else:
+            tof, k_hit = out
+            if (tof.shape != self._shape(G, self.E) or k_hit.shape != tof.shape or tof.dtype != np.float64 or
+                    k_hit.dtype != np.int32 or not tof.flags.c_contiguous or not k_hit.flags.c_contiguous):
+                raise ValueError("out must be C-contiguous (float64, int32) arrays of the table's shape")
         rec, out = None, {}
         if records:
             rec = _capi.RayRecords()

@@ -449,3 +449,17 @@ def test_other_material_and_lens_parameters(engine, oracle_dm, seed):
     assert np.array_equal(t.records["idx"], idx)
     assert np.array_equal(t.k_hit, k_hit.T) and np.array_equal(t.tof, tof.T)
     assert (idx >= 0).mean() > 0.3
+
+
+def test_pinned_output_buffers(engine):
+    """tof_table(out=...) with page-locked arrays from tofrt_host_alloc gives the same bytes."""
+    from ray_tracing_ultrasound_b200 import pinned_empty
+    x_a, z_a, alpha, zf = _std(engine)
+    radii, offsets = rs.synthetic_grid(64, 64)
+    t = engine.tof_table(radii, offsets)
+    tof, kh = pinned_empty((len(radii), 65)), pinned_empty((len(radii), 65), np.int32)
+    t2 = engine.tof_table(radii, offsets, out=(tof, kh))
+    assert t2.tof is tof and np.array_equal(tof, t.tof) and np.array_equal(kh, t.k_hit)
+    with pytest.raises(ValueError):
+        engine.tof_table(radii, offsets, out=(tof[:10], kh[:10]))
+    del tof, kh, t2
