@@ -148,6 +148,34 @@ __device__ __forceinline__ double refract(double phi_in, double dz, double dx, d
     return phi_slope - HALF_PI + theta_2;
 }
 
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (cp.async.bulk, sm_90+) ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
 // ---- prepare kernel: main_rt.py:338-349 for every launch angle ----------------
 __global__ void tofrt_prepare_kernel(DevSetup S, const double *alpha, double2 *lens, double *a_pq,
                                      double *b_pq, double *phi_pq, double *leg1, int *bad)
@@ -244,9 +272,20 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
     int *s_perm = reinterpret_cast<int *>(s_tof + (HG ? (size_t)0 : (size_t)kWarps * E));
     int *s_khit = s_perm + S.E_sorted;               // [kWarps][E] (absent when HG)
 
-    for (int i = threadIdx.x; i < Npad; i += kThreads) s_lens[i] = S.lens[i];
-    for (int i = threadIdx.x; i < K - 1; i += kThreads) s_seg[i] = S.seg[i];
+    // Stage the sampled surface once per CTA: two TMA bulk copies (lens samples, chords; 16-byte
+    // aligned, multiples of 16 bytes) complete on one mbarrier while the threads load the small
+    // receiver table themselves.
+    __shared__ __align__(8) unsigned long long s_bar;
+    const unsigned lens_bytes = (unsigned)Npad * (unsigned)sizeof(double2), seg_bytes = (unsigned)K * (unsigned)sizeof(double2);
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar, lens_bytes + seg_bytes);
+        tma_bulk_g2s(s_lens, S.lens, lens_bytes, &s_bar);
+        tma_bulk_g2s(s_seg, S.seg, seg_bytes, &s_bar);
+    }
     for (int i = threadIdx.x; i < S.E_sorted; i += kThreads) { s_xs[i] = S.xs[i]; s_perm[i] = S.perm[i]; }
+    while (!mbar_try_wait(&s_bar, 0)) {}
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1213,6 +1252,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     CUDA_TRY(cudaMalloc(&c->d_leg1, sizeof(double) * K * NS));
     CUDA_TRY(cudaMalloc(&c->d_lens, sizeof(double2) * S.Npad));
     CUDA_TRY(cudaMalloc(&c->d_seg, sizeof(double2) * K));
+    CUDA_TRY(cudaMemset(c->d_seg, 0, sizeof(double2) * K));  // entry K-1 is padding (TMA copies K entries)
     CUDA_TRY(cudaMalloc(&c->d_xrx, sizeof(double) * E));
     CUDA_TRY(cudaMalloc(&c->d_sh, sizeof(double) * 2 * NS));
     CUDA_TRY(cudaMemcpy(c->d_sh, x_shooters, sizeof(double) * NS, cudaMemcpyHostToDevice));
