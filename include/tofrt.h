@@ -101,6 +101,13 @@ int tofrt_setup_shooters(tofrt_ctx *ctx, const tofrt_params *params, const doubl
 #define TOFRT_OPT_SEARCH 1
 #define TOFRT_SEARCH_SCAN 0
 #define TOFRT_SEARCH_GUIDED 1
+/* TOFRT_OPT_SURFACE (extension, parity unpinned -- BASELINE configs 1-2 name a "flat interface" the
+ * reference does not have): TOFRT_SURFACE_LENS = the reference's constant-TOF lens h(alpha)
+ * (main_rt.py:180-214, default); TOFRT_SURFACE_FLAT = the plane z = h0, sampled at the same angles
+ * (h = h0 / cos(alpha)).  Set it BEFORE tofrt_setup; changing it invalidates the current setup. */
+#define TOFRT_OPT_SURFACE 2
+#define TOFRT_SURFACE_LENS 0
+#define TOFRT_SURFACE_FLAT 1
 int tofrt_set_option(tofrt_ctx *ctx, int option, int value);
 
 /* Facts about the current setup: TOFRT_INFO_SHAPE -> +1 concave / -1 convex /

@@ -57,6 +57,10 @@ class Oracle:
         l0, h0 = np.float64(l0), np.float64(h0)
         return Params(float(c1), float(c2), float(l0), float(h0), float(l0 + h0))
 
+    def set_surface(self, flat):
+        """Extension: flat interface z = h0 instead of the reference's lens (process-wide switch)."""
+        self.lib.tofo_set_surface(ctypes.c_int(1 if flat else 0))
+
     def max_threads(self):
         return int(self.lib.tofo_max_threads())
 

@@ -76,6 +76,8 @@ struct DevSetup {
     int guided;     // search mode: 1 = guided (bracketed) search, 0 = the reference's literal O(N) scan
     int log2n;      // ceil(log2(K)) + 1 bisection steps
     double X, Z;    // max |x_p|, max |z_p|  (rounding-error bound of a diff)
+    int surface;    // 0: the reference's constant-TOF lens h(alpha); 1: flat interface z = h0 (extension)
+    double h0;
     // tables in global memory
     const double2 *lens;   // [Npad] (x_p, z_p), padded with copies of the last sample
     const double2 *seg;    // [K-1] chord (m_seg, b_seg) of main_rt.py:127-128
@@ -124,19 +126,32 @@ __device__ __forceinline__ double dist2d(double x1, double z1, double x2, double
 __device__ __forceinline__ double line_diff(double2 s, double m, double b) { return s.y - (m * s.x + b); }
 
 // h(alpha), dz/dalpha, dx/dalpha (main_rt.py:180-234); B of :184 and :203 are the same bits
-__device__ __forceinline__ void lens_point(const DevSetup &S, double sn, double cs, double *h, double *dz,
-                                           double *dx)
+template <bool FLAT>
+__device__ __forceinline__ void lens_point_t(const DevSetup &S, double sn, double cs, double *h, double *dz,
+                                             double *dx)
 {
-    double B = S.twod * cs - S.K2;
-    double sd = sqrt(B * B - S.fourAC);
-    double hh = (-B - sd) / S.twoA;
-    double dB = -S.twod * sn;
-    double dB2 = 2 * B * dB;
-    double dS = (1 / (2 * sd)) * dB2;
-    double dh = S.phi1 * (dB + dS);
+    double hh, dh;
+    if (!FLAT) {
+        double B = S.twod * cs - S.K2;
+        double sd = sqrt(B * B - S.fourAC);
+        hh = (-B - sd) / S.twoA;
+        double dB = -S.twod * sn;
+        double dB2 = 2 * B * dB;
+        double dS = (1 / (2 * sd)) * dB2;
+        dh = S.phi1 * (dB + dS);
+    } else {  // flat interface z = h0 in the same polar form: h = h0 / cos(alpha) (extension, no reference analogue)
+        hh = S.h0 / cs;
+        dh = S.h0 * sn / (cs * cs);
+    }
     *h = hh;
     *dz = dh * cs - hh * sn;
     *dx = dh * sn + hh * cs;
+}
+// run-time surface switch, for the kernels where it does not matter (setup, two-point solve)
+__device__ __forceinline__ void lens_point(const DevSetup &S, double sn, double cs, double *h, double *dz, double *dx)
+{
+    if (S.surface == 0) lens_point_t<false>(S, sn, cs, h, dz, dx);
+    else lens_point_t<true>(S, sn, cs, h, dz, dx);
 }
 
 // refraction of main_rt.py:267-280 with the tuple form of dzdx
@@ -259,7 +274,7 @@ __device__ __forceinline__ void chord_intersection(const double2 *lens, const do
 // HG: first-hit state in the output rows (global memory) instead of warp-private shared memory
 // GUIDED: compile the guided search (its rare fallback is then a plain per-ray exact scan) or the
 // warp-wide literal scan -- two lean instruction streams instead of one kernel carrying both.
-template <bool HG, bool GUIDED>
+template <bool HG, bool GUIDED, bool FLAT>
 __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel(DevSetup S, TableArgs T)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -502,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                 double alpha_i = tofrt_atan2(ix, iz);
                 double sn, cs, h, dz, dx;
                 tofrt_sincos(alpha_i, &sn, &cs);
-                lens_point(S, sn, cs, &h, &dz, &dx);
+                lens_point_t<FLAT>(S, sn, cs, &h, &dz, &dx);
                 // refraction(phi_l, (dz, dx), c2, c1), main_rt.py:272-278
                 double phi_slope = tofrt_atan2(dz, dx);
                 double theta_1 = phi_l - (phi_slope + HALF_PI);
@@ -608,7 +623,8 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
 struct DevSetupF {
     float c1, c2, fourAC, twoA, twod, K2, phi1, c1_over_c2;
     float rtol, atol, tol_max, rx_min, rx_max, X, Z;
-    int K, E, E_sorted, has_nonfinite_rx, shape, log2n, n_shooters;
+    int K, E, E_sorted, has_nonfinite_rx, shape, log2n, n_shooters, surface;
+    float h0;
     const float2 *lens, *seg;
     const float *a_pq, *b_pq, *phi_pq, *z_f, *leg1, *x_rx, *xs;
     const int *perm;
@@ -834,12 +850,18 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
                 float alpha_i = atan2_f(ix, iz);
                 float sn, cs;
                 sincos_f(alpha_i, &sn, &cs);
-                float B = S.twod * cs - S.K2;
-                float sd = fsqrt_fast(B * B - S.fourAC);
-                float hh = __fdividef(-B - sd, S.twoA);
-                float dB = -S.twod * sn;
-                float dS = __fdividef(1.0f, 2 * sd) * (2 * B * dB);
-                float dh = S.phi1 * (dB + dS);
+                float hh, dh;
+                if (S.surface == 0) {
+                    float B = S.twod * cs - S.K2;
+                    float sd = fsqrt_fast(B * B - S.fourAC);
+                    hh = __fdividef(-B - sd, S.twoA);
+                    float dB = -S.twod * sn;
+                    float dS = __fdividef(1.0f, 2 * sd) * (2 * B * dB);
+                    dh = S.phi1 * (dB + dS);
+                } else {
+                    hh = __fdividef(S.h0, cs);
+                    dh = __fdividef(S.h0 * sn, cs * cs);
+                }
                 float dz = dh * cs - hh * sn, dx = dh * sn + hh * cs;
                 float phi_slope = atan2_f(dz, dx);
                 float theta_1 = phi_l - (phi_slope + HALF_PI_F);
@@ -1099,6 +1121,7 @@ struct tofrt_ctx {
     double *d_alpha = nullptr, *d_zf = nullptr, *d_a = nullptr, *d_b = nullptr, *d_phi = nullptr, *d_leg1 = nullptr;
     double2 *d_lens = nullptr, *d_seg = nullptr;
     int opt_guided = 1;
+    int opt_surface = 0;
     float *d_f32 = nullptr;   // FP32 copies of the tables (FP32 mode)
     DevSetupF SF{};
     size_t smem_f32 = 0;
@@ -1210,6 +1233,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     S.c2_over_c1 = p->c2 / p->c1;
     S.c1_over_c2 = p->c1 / p->c2;
     S.n_shooters = NS;
+    S.surface = c->opt_surface; S.h0 = p->h0;
     S.rtol = rtol; S.atol = atol;
     S.K = K; S.E = E;
     S.Npad = 1 + ((K - 1 + kChunk - 1) / kChunk) * kChunk;
@@ -1300,7 +1324,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
             if (!(b2 - a > guard)) inc = false;
         }
         S.X = X; S.Z = Z;
-        S.shape = (S.tables_ok && incr && K >= 3) ? (dec ? 1 : (inc ? -1 : 0)) : 0;
+        S.shape = (S.tables_ok && incr && K >= 3 && S.surface == 0) ? (dec ? 1 : (inc ? -1 : 0)) : 0;
         int lg = 1;
         while ((1 << lg) < K) ++lg;
         S.log2n = lg + 1;
@@ -1332,7 +1356,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
         F.tol_max = (float)(S.tol_max * 1.001) + 1e-30f;
         F.rx_min = (float)S.rx_min; F.rx_max = (float)S.rx_max; F.X = (float)S.X * 1.0001f; F.Z = (float)S.Z * 1.0001f;
         F.K = K; F.E = E; F.E_sorted = S.E_sorted; F.has_nonfinite_rx = S.has_nonfinite_rx;
-        F.shape = S.shape; F.log2n = S.log2n; F.n_shooters = NS;
+        F.shape = S.shape; F.log2n = S.log2n; F.n_shooters = NS; F.surface = S.surface; F.h0 = (float)S.h0;
         c->SF = F;
         c->smem_f32 = (size_t)2 * K * sizeof(float2) + (size_t)S.E_sorted * (sizeof(float) + sizeof(int)) +
                       (size_t)kWarps * E * (sizeof(float) + sizeof(int)) + 16;
@@ -1343,16 +1367,20 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
         CUDA_TRY(cudaDeviceSynchronize());
     }
 
-    if (S.hits_in_global) {
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (S.surface != 0 && S.hits_in_global)
+        return fail(TOFRT_E_TOOLARGE, "tofrt_setup: the flat-interface extension supports the shared-memory receiver budget only");
+    if (S.surface != 0) {
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    } else if (S.hits_in_global) {
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     } else {
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     int occ = 1;
-    if (S.hits_in_global) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<true, true>, kThreads, smem));
-    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<false, true>, kThreads, smem));
+    if (S.hits_in_global) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<true, true, false>, kThreads, smem));
+    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<false, true, false>, kThreads, smem));
     c->ctas_per_sm = std::max(1, occ);
     c->S = S; c->K = K; c->E = E; c->smem = smem; c->n_shooters = NS; c->params_d = p->d;
     c->ready = true;
@@ -1367,6 +1395,13 @@ int tofrt_set_option(tofrt_ctx *c, int option, int value)
             return fail(TOFRT_E_BADARG, "tofrt_set_option: bad search mode");
         c->opt_guided = value;
         c->S.guided = value;
+        return TOFRT_OK;
+    }
+    if (option == TOFRT_OPT_SURFACE) {
+        if (value != TOFRT_SURFACE_LENS && value != TOFRT_SURFACE_FLAT)
+            return fail(TOFRT_E_BADARG, "tofrt_set_option: bad surface type");
+        if (value != c->opt_surface) c->ready = false;  // the tables belong to the other surface: set up again
+        c->opt_surface = value;
         return TOFRT_OK;
     }
     return fail(TOFRT_E_BADARG, "tofrt_set_option: unknown option");
@@ -1422,12 +1457,14 @@ static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_
     long long warps_needed = G * s_count;
     int grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, (warps_needed + kWarps - 1) / kWarps);
     const bool guided = c->S.guided && c->S.shape != 0;
-    if (c->S.hits_in_global) {
-        if (guided) tofrt_table_kernel<true, true><<<grid, kThreads, c->smem, st>>>(c->S, T);
-        else tofrt_table_kernel<true, false><<<grid, kThreads, c->smem, st>>>(c->S, T);
+    if (c->S.surface != 0) {  // flat interface (extension): a plane has no strict curvature, literal scan only
+        tofrt_table_kernel<false, false, true><<<grid, kThreads, c->smem, st>>>(c->S, T);
+    } else if (c->S.hits_in_global) {
+        if (guided) tofrt_table_kernel<true, true, false><<<grid, kThreads, c->smem, st>>>(c->S, T);
+        else tofrt_table_kernel<true, false, false><<<grid, kThreads, c->smem, st>>>(c->S, T);
     } else {
-        if (guided) tofrt_table_kernel<false, true><<<grid, kThreads, c->smem, st>>>(c->S, T);
-        else tofrt_table_kernel<false, false><<<grid, kThreads, c->smem, st>>>(c->S, T);
+        if (guided) tofrt_table_kernel<false, true, false><<<grid, kThreads, c->smem, st>>>(c->S, T);
+        else tofrt_table_kernel<false, false, false><<<grid, kThreads, c->smem, st>>>(c->S, T);
     }
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
@@ -1804,7 +1841,7 @@ int tofrt_kernel_info(tofrt_ctx *c, int *grid, int *block, int *smem_bytes, int 
 {
     if (!c) return fail(TOFRT_E_BADARG, "tofrt_kernel_info: ctx is NULL");
     cudaFuncAttributes fa{};
-    CUDA_TRY(cudaFuncGetAttributes(&fa, tofrt_table_kernel<false, true>));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, tofrt_table_kernel<false, true, false>));
     if (grid) *grid = c->sm_count * c->ctas_per_sm;
     if (block) *block = kThreads;
     if (smem_bytes) *smem_bytes = (int)c->smem;

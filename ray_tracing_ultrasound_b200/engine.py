@@ -96,6 +96,12 @@ class TofEngine:
     def _shape(self, G, last):
         return (self.S, G, last) if self.multi else (G, last)
 
+    def set_surface(self, kind):
+        """'lens' (the reference's constant-TOF lens, default) or 'flat' (plane z = h0; extension).
+        Call before setup()."""
+        _capi.check(self._lib.tofrt_set_option(self._ctx, 2, {"lens": 0, "flat": 1}[kind]))
+        return self
+
     def set_search(self, mode):
         """'guided' (default) or 'scan' (the reference's literal O(N) search); same results."""
         value = {"scan": 0, "guided": 1}[mode]

@@ -10,12 +10,15 @@ from scipy.optimize import brentq
 
 
 class Lens:
-    def __init__(self, c1=6400.0, c2=1483.0, l0=0.12156646438729327, h0=0.08843353561270673):
+    def __init__(self, c1=6400.0, c2=1483.0, l0=0.12156646438729327, h0=0.08843353561270673, flat=False):
+        self.flat = flat  # extension: plane z = h0 instead of the reference's lens
         self.c1, self.c2 = np.float64(c1), np.float64(c2)
         self.l0, self.h0 = np.float64(l0), np.float64(h0)
         self.d = self.l0 + self.h0
 
     def h(self, alpha):
+        if self.flat:
+            return self.h0 / np.cos(alpha)
         c1, c2, d = self.c1, self.c2, self.d
         T = self.l0 / c1 + self.h0 / c2
         A = (np.square(c1) / np.square(c2)) - 1
@@ -24,6 +27,8 @@ class Lens:
         return (-B - np.sqrt(np.square(B) - 4 * A * C)) / (2 * A)
 
     def dh(self, alpha):
+        if self.flat:
+            return self.h0 * np.sin(alpha) / (np.cos(alpha) * np.cos(alpha))
         c1, c2, d = self.c1, self.c2, self.d
         T = self.l0 / c1 + self.h0 / c2
         A = (np.square(c1) / np.square(c2)) - 1
