@@ -971,8 +971,15 @@ __global__ void __launch_bounds__(kFermatThreads) tofrt_fermat_kernel(DevSetup S
     const int N = S.K;
     double2 *s_lens = reinterpret_cast<double2 *>(smem_raw);
     double *s_d1 = reinterpret_cast<double *>(s_lens + N);
+    float2 *s_lens32 = reinterpret_cast<float2 *>(s_d1 + N);  // float copies for the screening pass
+    float *s_d132 = reinterpret_cast<float *>(s_lens32 + N);
     __shared__ unsigned long long s_item;
-    for (int i = threadIdx.x; i < N; i += kFermatThreads) s_lens[i] = S.lens[i];
+    __shared__ float s_d1max;
+    for (int i = threadIdx.x; i < N; i += kFermatThreads) {
+        const double2 p = S.lens[i];
+        s_lens[i] = p;
+        s_lens32[i] = make_float2((float)p.x, (float)p.y);
+    }
     const long long tiles = (A.F + kFermatThreads - 1) / kFermatThreads;
     const unsigned long long items = (unsigned long long)tiles * S.E;
     const double inv_c2 = 1.0 / S.c2;
@@ -986,7 +993,16 @@ __global__ void __launch_bounds__(kFermatThreads) tofrt_fermat_kernel(DevSetup S
         const int e = (int)(item / tiles);
         const long long f = (long long)(item % tiles) * kFermatThreads + threadIdx.x;
         if (e != cur_e) {  // uniform across the CTA
-            for (int i = threadIdx.x; i < N; i += kFermatThreads) s_d1[i] = A.d1[(size_t)e * N + i];
+            if (threadIdx.x == 0) s_d1max = 0.f;
+            __syncthreads();
+            float mx = 0.f;
+            for (int i = threadIdx.x; i < N; i += kFermatThreads) {
+                const double v = A.d1[(size_t)e * N + i];
+                s_d1[i] = v;
+                s_d132[i] = (float)v;
+                mx = fmaxf(mx, (float)fabs(v));
+            }
+            atomicMax(reinterpret_cast<int *>(&s_d1max), __float_as_int(mx));  // non-negative floats order as ints
             cur_e = e;
             __syncthreads();
         }
@@ -994,14 +1010,37 @@ __global__ void __launch_bounds__(kFermatThreads) tofrt_fermat_kernel(DevSetup S
         const double fx = A.fx[f], fz = A.fz[f];
         const double ax = S.x_rx[e], az = A.z_el;
         // ---- discrete argmin over the sampled surface (first minimum on ties) ----
+        // Exact FP64 argmin, found with an FP32 screening pass: t32_j differs from t_j by less than
+        // delta = 2^-19 (D/c2 + max_j d1_j), D = X + Z + |fx| + |fz| (float rounding of the four
+        // coordinates, of the squared distance, the approximate square root and the fma; >2.5x margin),
+        // so the exact minimiser is among the samples with t32_j <= min_j t32_j + 2 delta -- a handful
+        // around the minimum -- and only those are evaluated in FP64, in index order.
         double best = INFINITY;
         int jbest = 0;
+        {
+            const float fx32 = (float)fx, fz32 = (float)fz, ic2 = (float)inv_c2;
+            float min32 = INFINITY;
 #pragma unroll 4
-        for (int j = 0; j < N; ++j) {
-            const double2 p = s_lens[j];
-            const double ux = p.x - fx, uz = p.y - fz;
-            const double t = fma(sqrt(fma(ux, ux, uz * uz)), inv_c2, s_d1[j]);
-            if (t < best) { best = t; jbest = j; }
+            for (int j = 0; j < N; ++j) {
+                const float2 p = s_lens32[j];
+                const float ux = p.x - fx32, uz = p.y - fz32;
+                min32 = fminf(min32, fmaf(fsqrt_fast(fmaf(ux, ux, uz * uz)), ic2, s_d132[j]));
+            }
+            const float D = (float)(S.X + S.Z + fabs(fx) + fabs(fz));
+            const float thr = min32 + 2.0f * 1.9073486328125e-06f * (D * ic2 + s_d1max) * 1.0001f;
+            const bool screened = thr == thr && thr < INFINITY;  // non-finite inputs: evaluate everything exactly
+#pragma unroll 2
+            for (int j = 0; j < N; ++j) {
+                const float2 p = s_lens32[j];
+                const float ux32 = p.x - fx32, uz32 = p.y - fz32;
+                const float t32 = fmaf(fsqrt_fast(fmaf(ux32, ux32, uz32 * uz32)), ic2, s_d132[j]);
+                if (!screened || t32 <= thr) {
+                    const double2 q = s_lens[j];
+                    const double ux = q.x - fx, uz = q.y - fz;
+                    const double t = fma(sqrt(fma(ux, ux, uz * uz)), inv_c2, s_d1[j]);
+                    if (t < best) { best = t; jbest = j; }
+                }
+            }
         }
         // ---- continuous refinement between the neighbouring samples ----
         double a = A.alpha[max(jbest - 1, 0)], b = A.alpha[min(jbest + 1, N - 1)];
@@ -1756,7 +1795,7 @@ int tofrt_fermat_dev(tofrt_ctx *c, const double *d_fx, const double *d_fz, long 
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int K = c->K, E = c->E;
-    const size_t smem = (size_t)K * (sizeof(double2) + sizeof(double)) + 16;
+    const size_t smem = (size_t)K * (sizeof(double2) + sizeof(double) + sizeof(float2) + sizeof(float)) + 16;
     if (smem > 227 * 1024) return fail(TOFRT_E_TOOLARGE, "tofrt_fermat_dev: too many lens samples");
     if (!c->d_d1) {
         CUDA_TRY(cudaMalloc(&c->d_d1, sizeof(double) * (size_t)K * E));
