@@ -36,8 +36,8 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of tofrt_table_kernel from the committed
 # `ncu --set full` captures (profiles/), scaled to the full 1024x1024 grid; None until captured.
-# profiles/ncu_r1_table_kernel.json: 155.9 MB (guided) / 152.8 MB (scan) per 131 072-geometry launch
-NCU_TRAFFIC_BYTES = {"guided": 155.9e6 * 8, "scan": 152.8e6 * 8}
+# profiles/ncu_r1_table_kernel.json: 148.6 MB (guided) / 152.1 MB (scan) per 131 072-geometry launch
+NCU_TRAFFIC_BYTES = {"guided": 148.6e6 * 8, "scan": 152.1e6 * 8}
 
 METRIC = "ray-solves/sec (element x pixel)"
 UNIT = "ray-solves/s"
@@ -74,14 +74,33 @@ def algorithmic_ops(G, K, N, E):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (profiling recipe)."""
+    """SM clock + throttle reasons during the timed region (the profiling recipe's clocks line).
+    Reads NVML in-process (what nvidia-smi prints) every 20 ms; falls back to nvidia-smi."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
-        self.max_mhz = None
+        self.max_mhz, self.source = None, "nvml"
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            bits = int(get_reasons(h))
+            for bit, name in self.REASONS.items():
+                if bits & bit:
+                    self.reasons.add(name)
+            time.sleep(0.02)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -99,9 +118,16 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.05)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
-                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "source": self.source}
 
 
 def cpu_port_rate(x_a, z_a, alpha, zf, radii, offsets, target_s=8.0):
@@ -357,7 +383,7 @@ def main():
             "roofline_guided": {"kernel_ms": mode_ms["guided"], "achieved": ops / (mode_ms["guided"] * 1e-3) / 1e12,
                                 "frac": ops / (mode_ms["guided"] * 1e-3) / peak_issue},
             "modes_identical": other_same,
-            "fp64_pipe_active_pct_ncu": {"guided": 55.3, "scan": 62.1,
+            "fp64_pipe_active_pct_ncu": {"guided": 56.4, "scan": 61.8,
                                          "source": "profiles/ncu_r1_table_kernel.json (sm__inst_executed_pipe_fp64, "
                                                    "one --set full capture per mode)"},
             "peak_source": "tofrt_measure_fp64_peak on this GPU (un-fused DMUL+DADD thread-instructions/s); "
