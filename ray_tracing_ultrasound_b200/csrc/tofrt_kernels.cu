@@ -74,7 +74,7 @@ struct DevSetup {
     int hits_in_global;  // 1: E too large for the per-warp shared-memory first-hit state -> keep it in the output rows
     int shape;      // +1: sampled lens strictly concave in x, -1: strictly convex, 0: neither (no guided search)
     int guided;     // search mode: 1 = guided (bracketed) search, 0 = the reference's literal O(N) scan
-    int log2n;      // ceil(log2(K)) + 1 bisection steps
+    int log2n;      // ceil(log2(K)) bisection steps
     double X, Z;    // max |x_p|, max |z_p|  (rounding-error bound of a diff)
     int surface;    // 0: the reference's constant-TOF lens h(alpha); 1: flat interface z = h0 (extension)
     double h0;
@@ -93,6 +93,7 @@ struct TableArgs {
     double *tof;
     int *k_hit;
     tofrt_ray_records rec;
+    int any_rec;           // any per-ray record requested (besides legs)
     int s_begin, s_count;  // shooters [s_begin, s_begin + s_count) of the setup; outputs are [s_count][G][...]
     const double *inject_m, *inject_b;  // test hook (tofrt_debug_search_host): replace the reflected line of ray [w][k]
     unsigned long long *counter;
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
     khit_t *w_khit = s_khit + (size_t)warp * E;
     const int nchunks = (K + 31) >> 5;
     const unsigned FULL = 0xffffffffu;
+    const double cand_lo = S.rx_min - S.tol_max, cand_hi = S.rx_max + S.tol_max;  // aperture +- largest tolerance
     unsigned st_rays = 0, st_scan_rays = 0, st_scan_warps = 0, st_onsample = 0;
 
     for (;;) {
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                     lo = (act && cond) ? mid : lo;
                     hi = (act && !cond) ? mid : hi;
                 }
+                if (bracket && hi - lo > 1) { bracket = false; }  // cannot happen (log2n steps suffice); scan if it did
                 if (bracket && neg0) {
                     // hi = lo + 1 failed the test (or is the untested last sample).  If g_hi is still
                     // certainly negative, hi is at/after the maximum while lo is before it: g_hi IS
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
             }
 
             // ---- optional per-ray records ----
-            if (valid) {
+            if (T.any_rec && valid) {  // one uniform test in table-only mode
                 size_t o = (size_t)w * K + k;
                 if (T.rec.pipe_x) T.rec.pipe_x[o] = x_q;
                 if (T.rec.pipe_z) T.rec.pipe_z[o] = z_q;
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
             // candidates: finite receivers within tol_max of target_x (binary search in the
             // sorted copy); the exact np.isclose decides.  +-inf landing points can only match
             // an identical infinite receiver.
-            bool cand = valid && target_x >= S.rx_min - S.tol_max && target_x <= S.rx_max + S.tol_max;
+            bool cand = valid && target_x >= cand_lo && target_x <= cand_hi;
             bool special = valid && S.has_nonfinite_rx && isinf(target_x);
             const bool want_legs = T.rec.legs != nullptr;
             if (__any_sync(FULL, cand || special || want_legs)) {
@@ -806,6 +809,7 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
                     lo = (act && cond) ? mid : lo;
                     hi = (act && !cond) ? mid : hi;
                 }
+                if (bracket && hi - lo > 1) bracket = false;
                 if (bracket && neg0) {
                     const float ghi = sh * line_diff_f(s_lens[hi], m, b), glo = sh * line_diff_f(s_lens[lo], m, b);
                     if (ghi < -tol) { bracket = false; none = true; edge = -fmaxf(ghi, glo) - tol; }
@@ -1366,7 +1370,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
         S.shape = (S.tables_ok && incr && K >= 3 && S.surface == 0) ? (dec ? 1 : (inc ? -1 : 0)) : 0;
         int lg = 1;
         while ((1 << lg) < K) ++lg;
-        S.log2n = lg + 1;
+        S.log2n = lg;  // ceil-halving an interval of length K-1 <= 2^lg reaches length 1 in lg steps
     }
     S.guided = c->opt_guided;
     // ---- FP32 mode: the same tables rounded to float ----
@@ -1488,6 +1492,7 @@ static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_
     TableArgs T{};
     T.radius = d_radius; T.offset = d_offset; T.G = G; T.tof = d_tof; T.k_hit = d_k_hit;
     if (d_rec) T.rec = *d_rec;
+    T.any_rec = T.rec.pipe_x || T.rec.pipe_z || T.rec.lens2_x || T.rec.lens2_z || T.rec.target_x || T.rec.idx;
     T.s_begin = s_begin; T.s_count = s_count;
     T.inject_m = inject_m; T.inject_b = inject_b;
     T.counter = c->d_counter;
