@@ -50,4 +50,29 @@ ta, tb = a.records["target_x"], b.records["target_x"]
 out["guided_vs_scan_per_ray"] = {"geometries": n3, "rays": n3 * len(alpha),
                                  "idx_mismatches": int((a.records["idx"] != b.records["idx"]).sum()),
                                  "target_x_mismatches": int(((ta != tb) & ~(ta.isnan() & tb.isnan())).sum())}
+# (3) random setups: material speeds, lens dimensions, ray counts, arrays, shooters, tolerances
+n4 = int(os.environ.get("FUZZ_SETUPS", "24"))
+per = int(os.environ.get("FUZZ_SETUP_GEOMS", "20000"))
+bad = 0; rays = 0; t0 = time.time()
+for i in range(n4):
+    r4 = np.random.default_rng(5000 + i)
+    kw = dict(c1=r4.uniform(3000, 7000), c2=r4.uniform(900, 2500), l0=r4.uniform(0.05, 0.2), h0=r4.uniform(0.04, 0.12))
+    K = int(r4.integers(64, 2000)); nel = int(r4.choice([16, 64, 128, 256]))
+    d = float(np.float64(kw["l0"]) + np.float64(kw["h0"]))
+    xa, _ = rs.transducer(num_elements=nel, pitch=np.float64(r4.uniform(2e-4, 8e-4)), d=d)
+    al = np.linspace(-r4.uniform(0.3, 0.85), r4.uniform(0.3, 0.85), K)
+    zf4 = np.ones(K) * d
+    sh = int(r4.integers(0, len(xa)))
+    rtol, atol = 10.0 ** r4.uniform(-7, -4), 10.0 ** r4.uniform(-7, -4)
+    eng.setup(al, zf4, xa[sh], d, xa, rtol=rtol, atol=atol, **kw)
+    eng.set_search("guided" if i % 3 else "scan")
+    radii = r4.uniform(0.05, 1.1, per) * kw["h0"]; offsets = r4.uniform(-0.3, 0.3, per) * kw["h0"]
+    t = eng.tof_table(radii, offsets, records=("idx",))
+    p4 = o.params(**kw)
+    tof, k_hit, idx = o.table(p4, radii, offsets, xa[sh], d, zf4, al, xa, rtol=rtol, atol=atol, want_idx=True)
+    bad += int((t.records["idx"] != idx).sum()) + int((t.k_hit != k_hit.T).sum()) + int((t.tof != tof.T).sum())
+    rays += per * K
+out["random_setups_vs_twin_oracle"] = {"setups": n4, "geometries_per_setup": per, "rays": rays, "mismatches": bad,
+                                       "varied": "c1, c2, l0, h0, K in [64, 2000), 16-256 elements, pitch, aperture, shooter, rtol/atol, search mode",
+                                       "seconds": round(time.time() - t0, 1)}
 print(json.dumps(out, indent=1))
