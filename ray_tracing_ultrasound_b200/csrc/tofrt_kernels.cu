@@ -54,7 +54,10 @@ namespace {
 #endif
 constexpr int kThreads = TOFRT_THREADS;  // warps per CTA = kThreads / 32
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunk = 16;            // lens samples per early-exit check
+#ifndef TOFRT_SCAN_CHUNK
+#define TOFRT_SCAN_CHUNK 32
+#endif
+constexpr int kChunk = TOFRT_SCAN_CHUNK;  // lens samples per early-exit check of the literal scan (<= 32)
 constexpr int kNoHit = 0x7fffffff;
 #ifndef TOFRT_CHUNK_MB
 #define TOFRT_CHUNK_MB 64  // output bytes per pipelined chunk of tofrt_table_host

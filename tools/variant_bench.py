@@ -5,7 +5,7 @@
 import os, subprocess, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = {"t1024": ("TOFRT_THREADS=1024",), "t896": ("TOFRT_THREADS=896",), "t768": ("TOFRT_THREADS=768",)}
+VARIANTS = {"c16": ("TOFRT_SCAN_CHUNK=16",), "c32": ("TOFRT_SCAN_CHUNK=32",), "c8": ("TOFRT_SCAN_CHUNK=8",)}
 VDIR = os.path.join(ROOT, "tools", "_variants")
 
 if sys.argv[1] == "build":
