@@ -326,8 +326,9 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
         g64 = __shfl_sync(FULL, g64, 0);
         if (g64 >= (unsigned long long)T.G * (unsigned long long)T.s_count) break;
         const long long w = (long long)g64;               // work item = (shooter, geometry)
-        const long long g = w % T.G;
-        const size_t sk = (size_t)(T.s_begin + w / T.G) * K;  // offset of the shooter's per-ray tables
+        long long g = w, s_local = 0;
+        if (T.s_count > 1) { s_local = w / T.G; g = w - s_local * T.G; }  // 64-bit division only when several shooters
+        const size_t sk = (size_t)(T.s_begin + s_local) * K;  // offset of the shooter's per-ray tables
         const double r_outer = T.radius[g], pipe_offset = T.offset[g];
         const double rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset;
         if (HG) { w_tof = T.tof + (size_t)w * E; w_khit = T.k_hit + (size_t)w * E; }
