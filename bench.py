@@ -418,6 +418,9 @@ def main():
         if not args.no_cpu:
             v, threads, n, dt = cpu_port_rate(x_a, z_a, alpha, zf, radii, offsets)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "note": "C restatement of main_rt.py (oracle/), pthreads over geometries; the reference's "
+                                           "own NumPy path measured 35.6 ray-solves/s on one core of the build container "
+                                           "(BASELINE.md section 2) and cannot travel to the GPU box",
                                    "sample": f"{n} of {G} geometries, evenly strided, {dt:.1f} s, oracle C port "
                                              f"(glibc libm), E={E}, K=N={K}"}
         print(json.dumps(out))
