@@ -166,6 +166,32 @@ int tofrt_fermat_dev(tofrt_ctx *ctx, const double *d_fx, const double *d_fz, lon
 int tofrt_fermat_host(tofrt_ctx *ctx, const double *fx, const double *fz, long long F, double *tof,
                       int *kmin, double *alpha);
 
+/* 3-D two-point solve (BASELINE.json config 5 "32x32 matrix array, 3-D volume
+ * through a curved surface").  The reference is strictly 2-D (main_rt.py works in the x-z plane
+ * only), so no line of it corresponds to these entry points: PARITY UNPINNED.  What is reused is the
+ * lens profile of the current tofrt_setup (h_from_alpha, main_rt.py:180-189; or the flat-interface
+ * option): the 3-D lens is its surface of revolution about the z axis, P = h(alpha) n with
+ * n(a, b) = (sin a cos b, sin b, cos a cos b), cos(alpha) = cos a cos b -- b = 0 is the reference's
+ * plane with a = alpha.  For every (element e at (ex[e], ey[e], d), voxel (fx, fy, fz)) pair the
+ * entry point minimising |A_e - P|/c1 + |P - F|/c2 is found by a discrete search over the
+ * n_side x n_side grid of surface samples (ang[i], ang[j]) followed by a projected Newton
+ * refinement inside [ang[0], ang[n_side-1]]^2.
+ *   tofrt_fermat3d_setup   host pointers; builds the per-element sample tables on the device.
+ *   tofrt_fermat3d_dev     device pointers, asynchronous on `stream`.  Element-major outputs:
+ *                          tof[e*F + f]; kmin[e*F + f] = ia*n_side + ib of the best grid sample
+ *                          (FP32 search: on a near-tie of two samples either may be reported;
+ *                          the refined result is the same); ab[2*(e*F + f) + {0,1}] = refined
+ *                          entry angles.  kmin and ab may be NULL.
+ *   tofrt_fermat3d_host    host pointers, chunked and pipelined like tofrt_table_host.
+ * Checked against tests/fermat3d_oracle.py (NumPy/SciPy), the oracle's bit-exact twin, the 2-D
+ * solver in the plane y = 0 and analytic known answers (tests/test_gpu_fermat3d.py). */
+int tofrt_fermat3d_setup(tofrt_ctx *ctx, const double *ang, int n_side, const double *ex, const double *ey,
+                         int E3);
+int tofrt_fermat3d_dev(tofrt_ctx *ctx, const double *d_fx, const double *d_fy, const double *d_fz, long long F,
+                       double *d_tof, int *d_kmin, double *d_ab, void *stream);
+int tofrt_fermat3d_host(tofrt_ctx *ctx, const double *fx, const double *fy, const double *fz, long long F,
+                        double *tof, int *kmin, double *ab);
+
 /* Test hook: apply the return-path search of find_line_curve_intersection (main_rt.py:78-99,
  * current setup, current TOFRT_OPT_SEARCH mode) to n arbitrary lines y = m[i] x + b[i].  Runs the
  * production kernel with the reflected lines replaced; idx[i] is encoded as in tofrt_ray_records;

@@ -117,3 +117,36 @@ class Oracle:
             ctypes.c_int(nthreads))
         assert rc == 0, rc
         return tof, k_hit, idx
+
+    # ---- 3-D two-point Fermat solve: CPU twin of the CUDA kernel (device-math build only) ----
+    def fermat3d(self, p, ang, ex, ey, z_el, fx, fy, fz):
+        """-> tof[E][F], kmin[E][F], ab[E][F][2], evals[E][F], gap[E][F]."""
+        assert self.device_math, "the 3-D twin exists in the device-math build only"
+        ang, ex, ey, fx, fy, fz = map(_f64, (ang, ex, ey, fx, fy, fz))
+        E, F = len(ex), len(fx)
+        tof, kmin = np.empty((E, F)), np.empty((E, F), dtype=np.int32)
+        ab, evals, gap = np.empty((E, F, 2)), np.empty((E, F), dtype=np.int32), np.empty((E, F))
+        rc = self.lib.tofo_fermat3d(ctypes.byref(p), _dp(ang), ctypes.c_int(len(ang)), _dp(ex), _dp(ey),
+                                    ctypes.c_int(E), ctypes.c_double(z_el), _dp(fx), _dp(fy), _dp(fz),
+                                    ctypes.c_int(F), _dp(tof), _ip(kmin), _dp(ab), _ip(evals), _dp(gap))
+        assert rc == 0, rc
+        return tof, kmin, ab, evals, gap
+
+    def fermat3d_from(self, p, ang, A, F, k):
+        """Refinement started from grid sample k -> (tof, a, b)."""
+        ang = _f64(ang)
+        t, ab = ctypes.c_double(), np.empty(2)
+        rc = self.lib.tofo_fermat3d_from(ctypes.byref(p), _dp(ang), ctypes.c_int(len(ang)),
+                                         *[ctypes.c_double(float(v)) for v in (*A, *F)], ctypes.c_int(int(k)),
+                                         ctypes.byref(t), _dp(ab))
+        assert rc == 0, rc
+        return t.value, ab[0], ab[1]
+
+    def fermat3d_eval(self, p, ang, a, b, A, F):
+        """t, gradient (2), Hessian (aa, ab, bb) of the travel time at (a, b)."""
+        ang, A, F = _f64(ang), _f64(A), _f64(F)
+        t, g, H = ctypes.c_double(), np.empty(2), np.empty(3)
+        rc = self.lib.tofo_fermat3d_eval(ctypes.byref(p), _dp(ang), ctypes.c_int(len(ang)), ctypes.c_double(a),
+                                         ctypes.c_double(b), _dp(A), _dp(F), ctypes.byref(t), _dp(g), _dp(H))
+        assert rc == 0
+        return t.value, g, H

@@ -41,6 +41,7 @@
 
 #include "../../include/tofrt.h"
 #include "tofrt_math.h"
+#include "tofrt_fermat3d.h"
 
 #define HALF_PI 1.5707963267948966 /* np.pi / 2 */
 
@@ -1076,6 +1077,98 @@ __global__ void __launch_bounds__(kFermatThreads) tofrt_fermat_kernel(DevSetup S
     }
 }
 
+// =====================================================================================
+// 3-D two-point Fermat solve (SURVEY.md row f4 / BASELINE config 5: matrix array, 3-D volume,
+// curved surface).  The reference is 2-D: parity unpinned.  The lens is the surface of revolution
+// of the reference's profile h(alpha); the per-pair arithmetic lives in tofrt_fermat3d.h (shared
+// with the oracle's twin).  For every (matrix-array element e, voxel F) pair:
+//   1. discrete search over a coarse n_side x n_side grid of surface samples: one thread per pair,
+//      the element's (P_s, |A_e - P_s|/c1) table broadcast from shared memory, FP32 arithmetic
+//      (the argmin only selects the start of step 2);
+//   2. projected Newton refinement in FP64, state in registers.
+// One CTA works on (element, 256 voxels) items; outputs are element-major tof[e][f] so a CTA
+// writes 2 KB runs.
+// =====================================================================================
+constexpr int kF3dThreads = 256;
+
+struct F3dArgs {
+    const double *fx, *fy, *fz;  // [F] voxels
+    long long F;
+    const float4 *smp;           // [E][ns] (P_s.x, P_s.y, P_s.z, |A_e - P_s| / c1)
+    const double *ang;           // [n_side]
+    const double *ex, *ey;       // [E] element positions on the plane z = z_el
+    int E, n_side;
+    double z_el, cell;
+    double *tof;                 // [E][F]
+    int *kmin;                   // [E][F] or null
+    double *ab;                  // [E][F][2] or null
+    unsigned long long *counter;
+};
+
+__global__ void tofrt_f3d_prepare_kernel(tofrt_surf3d S, F3dArgs A, float4 *smp)
+{
+    const int ns = A.n_side * A.n_side;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, e = blockIdx.y;
+    if (s >= ns) return;
+    double P[3];
+    tofrt_f3d_point(&S, A.ang[s / A.n_side], A.ang[s % A.n_side], P);
+    const double ux = P[0] - A.ex[e], uy = P[1] - A.ey[e], uz = P[2] - A.z_el;
+    const double d1 = sqrt(ux * ux + uz * uz + uy * uy) * S.inv_c1;
+    smp[(size_t)e * ns + s] = make_float4((float)P[0], (float)P[1], (float)P[2], (float)d1);
+}
+
+__global__ void __launch_bounds__(kF3dThreads) tofrt_fermat3d_kernel(tofrt_surf3d S, F3dArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *s_smp = reinterpret_cast<float4 *>(smem_raw);
+    __shared__ unsigned long long s_item;
+    const int ns = A.n_side * A.n_side;
+    const long long tiles = (A.F + kF3dThreads - 1) / kF3dThreads;
+    const unsigned long long items = (unsigned long long)tiles * A.E;
+    const float ic2 = (float)S.inv_c2;
+    int cur_e = -1;
+    for (;;) {
+        __syncthreads();  // previous item done with s_smp / s_item
+        if (threadIdx.x == 0) s_item = atomicAdd(A.counter, 1ull);
+        __syncthreads();
+        const unsigned long long item = s_item;
+        if (item >= items) break;
+        const int e = (int)(item / tiles);
+        const long long f = (long long)(item % tiles) * kF3dThreads + threadIdx.x;
+        if (e != cur_e) {  // uniform across the CTA; items are element-major, so this is rare
+            for (int i = threadIdx.x; i < ns; i += kF3dThreads) s_smp[i] = A.smp[(size_t)e * ns + i];
+            cur_e = e;
+            __syncthreads();
+        }
+        if (f >= A.F) continue;
+        const double Fp[3] = {A.fx[f], A.fy[f], A.fz[f]};
+        const double Ap[3] = {A.ex[e], A.ey[e], A.z_el};
+        // ---- discrete search over the sampled surface (first minimum on ties) ----
+        int kb = 0;
+        {
+            const float gx = (float)Fp[0], gy = (float)Fp[1], gz = (float)Fp[2];
+            float best = INFINITY;
+#pragma unroll 4
+            for (int s = 0; s < ns; ++s) {
+                const float4 p = s_smp[s];
+                const float ux = p.x - gx, uy = p.y - gy, uz = p.z - gz;
+                const float t = fmaf(fsqrt_fast(fmaf(ux, ux, fmaf(uy, uy, uz * uz))), ic2, p.w);
+                const bool lt = t < best;
+                best = lt ? t : best;
+                kb = lt ? s : kb;
+            }
+        }
+        // ---- continuous refinement ----
+        const int ia = kb / A.n_side, ib = kb - ia * A.n_side;
+        double t, a, b;
+        tofrt_f3d_refine(&S, A.ang[ia], A.ang[ib], A.cell, Ap, Fp, &t, &a, &b);
+        const size_t o = (size_t)e * A.F + f;
+        A.tof[o] = t;
+        if (A.kmin) A.kmin[o] = kb;
+        if (A.ab) reinterpret_cast<double2 *>(A.ab)[o] = make_double2(a, b);
+    }
+}
+
 // ---- sparse form of the table: only the hits, ordered by (row, receiver) -------------------
 // 97-98 % of the table entries are misses; a consumer on the host that only wants the hits gets
 // them as a list, which cuts the device->host traffic ~30x (the dense D2H is what limits the
@@ -1186,6 +1279,13 @@ struct tofrt_ctx {
     void *hw[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t hw_bytes[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double *d_d1 = nullptr;   // Fermat solver: |A_e - P_j|/c1, built lazily per setup
+    // 3-D two-point solve (tofrt_fermat3d_setup)
+    bool f3_ready = false;
+    tofrt_surf3d f3_S{};
+    int f3_E = 0, f3_n = 0;
+    double f3_cell = 0.0;
+    double *f3_geo = nullptr;   // ang[n] ex[E] ey[E]
+    float4 *f3_smp = nullptr;   // [E][n*n]
     void free_all()
     {
         cudaFree(d_alpha); cudaFree(d_zf); cudaFree(d_a); cudaFree(d_b); cudaFree(d_phi); cudaFree(d_leg1);
@@ -1232,6 +1332,7 @@ int tofrt_destroy(tofrt_ctx *c)
     c->free_all();
     cudaFree(c->d_counter);
     cudaFree(c->ws[0]); cudaFree(c->ws[1]); cudaFree(c->d_in); cudaFree(c->d_d1);
+    cudaFree(c->f3_geo); cudaFree(c->f3_smp);
     for (int i = 0; i < 10; ++i) cudaFree(c->hw[i]);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -1263,6 +1364,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     c->ready = false;
     c->free_all();
     cudaFree(c->d_d1); c->d_d1 = nullptr;
+    c->f3_ready = false;
     CUDA_TRY(cudaMalloc(&c->d_bad, sizeof(int)));
 
     DevSetup S{};
@@ -1851,6 +1953,139 @@ int tofrt_fermat_host(tofrt_ctx *c, const double *fx, const double *fz, long lon
     cudaFree(d_f); cudaFree(d_t); cudaFree(d_k); cudaFree(d_a);
     if (rc != TOFRT_OK) return rc;
     if (e != cudaSuccess) return fail(TOFRT_E_CUDA, std::string("tofrt_fermat_host: ") + cudaGetErrorString(e));
+    return TOFRT_OK;
+}
+
+// ---- 3-D two-point solve ------------------------------------------------------------------
+int tofrt_fermat3d_setup(tofrt_ctx *c, const double *ang, int n_side, const double *ex, const double *ey, int E3)
+{
+    if (!c || !ang || !ex || !ey) return fail(TOFRT_E_BADARG, "tofrt_fermat3d_setup: NULL argument");
+    if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_fermat3d_setup: call tofrt_setup first (it defines the lens)");
+    if (n_side < 2) return fail(TOFRT_E_TOOFEW, "Surface grid needs at least two samples per axis.");
+    if (E3 < 1) return fail(TOFRT_E_BADARG, "tofrt_fermat3d_setup: need at least one element");
+    const size_t ns = (size_t)n_side * n_side;
+    if (ns * sizeof(float4) > 200 * 1024) return fail(TOFRT_E_TOOLARGE, "tofrt_fermat3d_setup: n_side too large (<= 113)");
+    for (int i = 0; i + 1 < n_side; ++i)
+        if (!(ang[i + 1] > ang[i])) return fail(TOFRT_E_BADARG, "tofrt_fermat3d_setup: ang must increase strictly");
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->f3_ready = false;
+    cudaFree(c->f3_geo); cudaFree(c->f3_smp);
+    c->f3_geo = nullptr; c->f3_smp = nullptr;
+    CUDA_TRY(cudaMalloc(&c->f3_geo, sizeof(double) * ((size_t)n_side + 2 * (size_t)E3)));
+    CUDA_TRY(cudaMalloc(&c->f3_smp, sizeof(float4) * ns * (size_t)E3));
+    CUDA_TRY(cudaMemcpy(c->f3_geo, ang, sizeof(double) * n_side, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->f3_geo + n_side, ex, sizeof(double) * E3, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->f3_geo + n_side + E3, ey, sizeof(double) * E3, cudaMemcpyHostToDevice));
+    tofrt_surf3d S{};
+    S.inv_c1 = 1.0 / c->S.c1; S.inv_c2 = 1.0 / c->S.c2;
+    S.twod = c->S.twod; S.K2 = c->S.K2; S.fourAC = c->S.fourAC; S.twoA = c->S.twoA;
+    S.h0 = c->S.h0; S.surface = c->S.surface;
+    S.lo = ang[0]; S.hi = ang[n_side - 1];
+    c->f3_S = S; c->f3_E = E3; c->f3_n = n_side;
+    c->f3_cell = (S.hi - S.lo) / (n_side - 1);
+    F3dArgs A{};
+    A.ang = c->f3_geo; A.ex = c->f3_geo + n_side; A.ey = c->f3_geo + n_side + E3;
+    A.E = E3; A.n_side = n_side; A.z_el = c->params_d;
+    dim3 grid((unsigned)((ns + 127) / 128), (unsigned)E3);
+    tofrt_f3d_prepare_kernel<<<grid, 128>>>(S, A, c->f3_smp);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFuncSetAttribute(tofrt_fermat3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(ns * sizeof(float4))));
+    CUDA_TRY(cudaDeviceSynchronize());
+    c->f3_ready = true;
+    return TOFRT_OK;
+}
+
+int tofrt_fermat3d_dev(tofrt_ctx *c, const double *d_fx, const double *d_fy, const double *d_fz, long long F,
+                       double *d_tof, int *d_kmin, double *d_ab, void *stream)
+{
+    if (!c || F < 0) return fail(TOFRT_E_BADARG, "tofrt_fermat3d_dev: bad argument");
+    if (!c->ready || !c->f3_ready) return fail(TOFRT_E_NOSETUP, "tofrt_fermat3d_dev: call tofrt_fermat3d_setup first");
+    if (F == 0) return TOFRT_OK;
+    if (!d_fx || !d_fy || !d_fz || !d_tof) return fail(TOFRT_E_BADARG, "tofrt_fermat3d_dev: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = c->f3_n, E3 = c->f3_E;
+    const size_t smem = (size_t)n * n * sizeof(float4);
+    F3dArgs A{};
+    A.fx = d_fx; A.fy = d_fy; A.fz = d_fz; A.F = F; A.smp = c->f3_smp;
+    A.ang = c->f3_geo; A.ex = c->f3_geo + n; A.ey = c->f3_geo + n + E3;
+    A.E = E3; A.n_side = n; A.z_el = c->params_d; A.cell = c->f3_cell;
+    A.tof = d_tof; A.kmin = d_kmin; A.ab = d_ab; A.counter = c->d_counter;
+    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_fermat3d_kernel, kF3dThreads, smem));
+    const long long items = ((F + kF3dThreads - 1) / kF3dThreads) * E3;
+    int grid = (int)std::min<long long>((long long)c->sm_count * std::max(1, occ), items);
+    tofrt_fermat3d_kernel<<<grid, kF3dThreads, smem, st>>>(c->f3_S, A);
+    CUDA_TRY(cudaGetLastError());
+    return TOFRT_OK;
+}
+
+// Host buffers: voxels are cut into chunks; chunk i is solved on one stream while the results of
+// chunk i-1 travel to the host on a second one (element-major outputs: strided 2-D copies).
+int tofrt_fermat3d_host(tofrt_ctx *c, const double *fx, const double *fy, const double *fz, long long F, double *tof,
+                        int *kmin, double *ab)
+{
+    if (!c || F < 0) return fail(TOFRT_E_BADARG, "tofrt_fermat3d_host: bad argument");
+    if (!c->ready || !c->f3_ready) return fail(TOFRT_E_NOSETUP, "tofrt_fermat3d_host: call tofrt_fermat3d_setup first");
+    if (F == 0) return TOFRT_OK;
+    if (!fx || !fy || !fz || !tof) return fail(TOFRT_E_BADARG, "tofrt_fermat3d_host: NULL buffer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t E3 = (size_t)c->f3_E, n = (size_t)F;
+    const size_t per_voxel = E3 * (sizeof(double) + (kmin ? sizeof(int) : 0) + (ab ? 2 * sizeof(double) : 0));
+    size_t chunk = std::max<size_t>(256, (((size_t)TOFRT_CHUNK_MB << 20) / per_voxel) / 256 * 256);
+    chunk = std::min(chunk, n);
+    if (!c->s_compute) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        }
+    }
+    double *d_f = nullptr;
+    char *slot[2] = {nullptr, nullptr};
+    const size_t slot_bytes = chunk * per_voxel + 3 * 256;
+    cudaError_t e = cudaMalloc(&d_f, sizeof(double) * 3 * n);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&slot[i], slot_bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_f, fx, sizeof(double) * n, cudaMemcpyHostToDevice, c->s_compute);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_f + n, fy, sizeof(double) * n, cudaMemcpyHostToDevice, c->s_compute);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_f + 2 * n, fz, sizeof(double) * n, cudaMemcpyHostToDevice, c->s_compute);
+    int rc = TOFRT_OK;
+    size_t i = 0;
+    for (size_t done = 0; done < n && e == cudaSuccess && rc == TOFRT_OK; done += chunk, ++i) {
+        const size_t m = std::min(chunk, n - done);
+        const int sl = (int)(i & 1);
+        char *base = slot[sl];
+        auto take = [&](size_t bytes) { char *q = base; base += (bytes + 255) / 256 * 256; return q; };
+        double *d_t = (double *)take(m * E3 * sizeof(double));
+        int *d_k = kmin ? (int *)take(m * E3 * sizeof(int)) : nullptr;
+        double *d_ab = ab ? (double *)take(m * E3 * 2 * sizeof(double)) : nullptr;
+        if (i >= 2) e = cudaStreamWaitEvent(c->s_compute, c->ev_free[sl], 0);
+        if (e != cudaSuccess) break;
+        rc = tofrt_fermat3d_dev(c, d_f + done, d_f + n + done, d_f + 2 * n + done, (long long)m, d_t, d_k, d_ab,
+                                (void *)c->s_compute);
+        if (rc != TOFRT_OK) break;
+        e = cudaEventRecord(c->ev_done[sl], c->s_compute);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_copy, c->ev_done[sl], 0);
+        // device chunk is [E][m]; host table is [E][F]
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(tof + done, n * sizeof(double), d_t, m * sizeof(double), m * sizeof(double), E3,
+                                  cudaMemcpyDeviceToHost, c->s_copy);
+        if (e == cudaSuccess && kmin)
+            e = cudaMemcpy2DAsync(kmin + done, n * sizeof(int), d_k, m * sizeof(int), m * sizeof(int), E3,
+                                  cudaMemcpyDeviceToHost, c->s_copy);
+        if (e == cudaSuccess && ab)
+            e = cudaMemcpy2DAsync(ab + 2 * done, n * 2 * sizeof(double), d_ab, m * 2 * sizeof(double),
+                                  m * 2 * sizeof(double), E3, cudaMemcpyDeviceToHost, c->s_copy);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev_free[sl], c->s_copy);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c->s_compute), e2 = cudaStreamSynchronize(c->s_copy);
+    cudaFree(d_f); cudaFree(slot[0]); cudaFree(slot[1]);
+    if (rc != TOFRT_OK) return rc;
+    if (e == cudaSuccess) e = e1 != cudaSuccess ? e1 : e2;
+    if (e != cudaSuccess) return fail(TOFRT_E_CUDA, std::string("tofrt_fermat3d_host: ") + cudaGetErrorString(e));
     return TOFRT_OK;
 }
 

@@ -278,6 +278,53 @@ class TofEngine:
                                                ctypes.c_void_p(stream)))
         return (tof, kmin, alpha) if with_alpha else (tof, kmin)
 
+    # ---- 3-D two-point solve (extension, SURVEY row f4 / BASELINE config 5; parity unpinned) ----
+    def setup_fermat3d(self, ex, ey, n_side=17, ang=None):
+        """Matrix-array elements (ex[e], ey[e], d) and the n_side x n_side grid of surface samples
+        (default: np.linspace over the launch-angle range of setup()) for fermat3d_tof."""
+        ex, ey = _f64(ex).ravel(), _f64(ey).ravel()
+        if ex.shape != ey.shape:
+            raise ValueError("ex and ey must have the same length")
+        if ang is None:
+            ang = np.linspace(self.alpha[0], self.alpha[-1], int(n_side))
+        ang = _f64(ang).ravel()
+        _capi.check(self._lib.tofrt_fermat3d_setup(self._ctx, ang.ctypes.data, len(ang), ex.ctypes.data,
+                                                   ey.ctypes.data, len(ex)))
+        self.f3_ang, self.f3_E = ang, len(ex)
+        return self
+
+    def fermat3d_tof(self, fx, fy, fz, with_kmin=True, with_angles=False):
+        """One-way travel time element -> lens -> voxel for every (element, voxel) pair:
+        (tof[E3, F][, kmin[E3, F]][, ab[E3, F, 2]]), host arrays."""
+        fx, fy, fz = _f64(fx).ravel(), _f64(fy).ravel(), _f64(fz).ravel()
+        if not (fx.shape == fy.shape == fz.shape):
+            raise ValueError("fx, fy and fz must have the same length")
+        F, E = len(fx), self.f3_E
+        tof = np.empty((E, F))
+        kmin = np.empty((E, F), dtype=np.int32) if with_kmin else None
+        ab = np.empty((E, F, 2)) if with_angles else None
+        _capi.check(self._lib.tofrt_fermat3d_host(self._ctx, fx.ctypes.data, fy.ctypes.data, fz.ctypes.data, F,
+                                                  tof.ctypes.data, kmin.ctypes.data if with_kmin else None,
+                                                  ab.ctypes.data if with_angles else None))
+        return tuple(x for x in (tof, kmin, ab) if x is not None) if (with_kmin or with_angles) else tof
+
+    def fermat3d_tof_cuda(self, fx, fy, fz, with_kmin=False, with_angles=False, out_tof=None):
+        """Same, device-resident torch tensors, asynchronous on the current stream."""
+        import torch
+        for v in (fx, fy, fz):
+            if not (v.is_cuda and v.dtype == torch.float64 and v.is_contiguous() and v.shape == fx.shape):
+                raise ValueError("fx/fy/fz must be contiguous float64 CUDA tensors of the same shape")
+        F, dev, E = fx.numel(), fx.device, self.f3_E
+        tof = out_tof if out_tof is not None else torch.empty((E, F), dtype=torch.float64, device=dev)
+        kmin = torch.empty((E, F), dtype=torch.int32, device=dev) if with_kmin else None
+        ab = torch.empty((E, F, 2), dtype=torch.float64, device=dev) if with_angles else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _capi.check(self._lib.tofrt_fermat3d_dev(self._ctx, fx.data_ptr(), fy.data_ptr(), fz.data_ptr(), F,
+                                                 tof.data_ptr(), kmin.data_ptr() if with_kmin else None,
+                                                 ab.data_ptr() if with_angles else None, ctypes.c_void_p(stream)))
+        res = tuple(x for x in (tof, kmin, ab) if x is not None)
+        return res if len(res) > 1 else tof
+
     # ---- main_rt.py:337-441 -----------------------------------------------------
     def shoot_rays(self, r_outer, pipe_offset, with_idx=False, with_legs=False):
         recs = ["pipe_x", "pipe_z", "lens2_x", "lens2_z", "target_x"]
