@@ -11,9 +11,9 @@
  *
  *     n(a, b) = (sin a cos b, sin b, cos a cos b)
  *
- * so b = 0 is the reference's x-z plane with a = alpha, where every quantity below reduces,
- * operation by operation, to the 2-D expressions of tofrt_kernels.cu (lens_point_t /
- * fermat_eval).  For an element A on the array plane and a focal point F in the water,
+ * so b = 0 is the reference's x-z plane with a = alpha, where the surface point has the bits of the
+ * 2-D lens_point_t of tofrt_kernels.cu.  For an element A on the array plane and a focal point F
+ * in the water,
  *
  *     t(a, b) = |A - P(a, b)| / c1 + |P(a, b) - F| / c2
  *
@@ -65,16 +65,30 @@ TOFRT_HD void tofrt_f3d_point(const tofrt_surf3d *S, double a, double b, double 
     P[0] = f * nx; P[1] = f * ny; P[2] = f * nz;
 }
 
+/* a*b + c*d and a*b + c*d + e*f with explicit fused steps (no reference operation order to keep
+ * here -- the reference has no 3-D code -- so the products are fused: half the FP64 instructions) */
+TOFRT_HD double tofrt_f3d_dot2(double a, double b, double c, double d) { return fma(a, b, c * d); }
+TOFRT_HD double tofrt_f3d_dot3(double a, double b, double c, double d, double e, double f)
+{
+    return fma(a, b, fma(c, d, e * f));
+}
+
 /* travel time of a given surface point */
 TOFRT_HD double tofrt_f3d_time(const tofrt_surf3d *S, const double P[3], const double A[3], const double F[3])
 {
     double ux = P[0] - A[0], uy = P[1] - A[1], uz = P[2] - A[2];
     double vx = P[0] - F[0], vy = P[1] - F[1], vz = P[2] - F[2];
-    double r1 = sqrt(ux * ux + uz * uz + uy * uy), r2 = sqrt(vx * vx + vz * vz + vy * vy);
-    return r1 * S->inv_c1 + r2 * S->inv_c2;
+    double r1 = sqrt(tofrt_f3d_dot3(ux, ux, uz, uz, uy, uy)), r2 = sqrt(tofrt_f3d_dot3(vx, vx, vz, vz, vy, vy));
+    return fma(r1, S->inv_c1, r2 * S->inv_c2);
 }
 
-/* t, gradient g = (t_a, t_b) and Hessian H = (t_aa, t_ab, t_bb) at (a, b) */
+/* t, gradient g = (t_a, t_b) and Hessian H = (t_aa, t_ab, t_bb) at (a, b).
+ * With P = f(n_z) n and the derivatives of the unit vector
+ *     n_a = (n_z, 0, -n_x)   n_b = (-sa sb, cb, -ca sb)   n_ab = (-ca sb, 0, sa sb)
+ *     n_aa = (-n_x, 0, -n_z) n_bb = -n                    (n_z)_a = -n_x, (n_z)_b = -ca sb
+ * every product u . P_x (u = P - A or P - F) is a combination of the five scalars u.n, u.n_a, u.n_b,
+ * u.n_ab, u.n_aa with the derivatives of f, and n.n_a = n.n_b = n_a.n_b = 0, |n_a| = cb, |n_b| = 1 give
+ * |P_a|^2 = f_a^2 + f^2 cb^2, P_a.P_b = f_a f_b, |P_b|^2 = f_b^2 + f^2: no derivative vector is formed. */
 TOFRT_HD void tofrt_f3d_eval(const tofrt_surf3d *S, double a, double b, const double A[3], const double F[3],
                              double *t, double g[2], double H[3])
 {
@@ -82,48 +96,41 @@ TOFRT_HD void tofrt_f3d_eval(const tofrt_surf3d *S, double a, double b, const do
     tofrt_sincos(a, &sa, &ca);
     tofrt_sincos(b, &sb, &cb);
     const double nx = sa * cb, ny = sb, nz = ca * cb;
+    const double sasb = sa * sb, casb = ca * sb;
     tofrt_f3d_radial(S, nz, &f, &f1, &f2);
     const double Px = f * nx, Py = f * ny, Pz = f * nz;
-    /* first derivatives of n; d(n_z)/da = na_z, d(n_z)/db = nb_z */
-    const double nax = nz, naz = -nx;                       /* na = (ca cb, 0, -sa cb) */
-    const double nbx = -sa * sb, nby = cb, nbz = -ca * sb;
-    const double ka = f1 * naz, kb = f1 * nbz;              /* df/da, df/db */
-    const double Pax = ka * nx + f * nax, Pay = ka * ny, Paz = ka * nz + f * naz;
-    const double Pbx = kb * nx + f * nbx, Pby = kb * ny + f * nby, Pbz = kb * nz + f * nbz;
-    /* second derivatives: n_aa = (-nx, 0, -nz), n_ab = (-ca sb, 0, sa sb), n_bb = -n;
-     * (n_z)_aa = -nz, (n_z)_ab = sa sb, (n_z)_bb = -nz */
-    const double sasb = sa * sb;
-    const double kaa = f2 * naz * naz - f1 * nz;
-    const double kab = f2 * naz * nbz + f1 * sasb;
-    const double kbb = f2 * nbz * nbz - f1 * nz;
-    const double Paax = kaa * nx + 2.0 * ka * nax - f * nx;
-    const double Paay = kaa * ny;
-    const double Paaz = kaa * nz + 2.0 * ka * naz - f * nz;
-    const double Pabx = kab * nx + (ka * nbx + kb * nax) - f * (ca * sb);
-    const double Paby = kab * ny + ka * nby;
-    const double Pabz = kab * nz + (ka * nbz + kb * naz) + f * sasb;
-    const double Pbbx = kbb * nx + 2.0 * kb * nbx - f * nx;
-    const double Pbby = kbb * ny + 2.0 * kb * nby - f * ny;
-    const double Pbbz = kbb * nz + 2.0 * kb * nbz - f * nz;
-    const double paa = Pax * Pax + Pay * Pay + Paz * Paz;
-    const double pab = Pax * Pbx + Pay * Pby + Paz * Pbz;
-    const double pbb = Pbx * Pbx + Pby * Pby + Pbz * Pbz;
+    const double ka = -(f1 * nx), kb = -(f1 * casb);       /* f_a, f_b */
+    const double f1nz = f1 * nz, f2nx = f2 * nx;
+    const double kaa = fma(f2nx, nx, -f1nz);               /* f_aa */
+    const double kab = fma(f2nx, casb, f1 * sasb);         /* f_ab */
+    const double kbb = fma(f2 * casb, casb, -f1nz);        /* f_bb */
+    const double ff = f * f;
+    const double paa = fma(ka, ka, ff * (cb * cb)), pab = ka * kb, pbb = fma(kb, kb, ff);
     double tt = 0.0, ga = 0.0, gb = 0.0, haa = 0.0, hab = 0.0, hbb = 0.0;
     for (int leg = 0; leg < 2; ++leg) {
         const double *X = leg ? F : A;
         const double ic = leg ? S->inv_c2 : S->inv_c1;
         const double ux = Px - X[0], uy = Py - X[1], uz = Pz - X[2];
-        const double r = sqrt(ux * ux + uz * uz + uy * uy);
+        const double r = sqrt(tofrt_f3d_dot3(ux, ux, uz, uz, uy, uy));
         const double ir = 1.0 / r;
         const double w = ir * ic, w3 = w * ir * ir;
-        const double ua = ux * Pax + uy * Pay + uz * Paz;
-        const double ub = ux * Pbx + uy * Pby + uz * Pbz;
-        tt += r * ic;
-        ga += ua * w;
-        gb += ub * w;
-        haa += (paa + (ux * Paax + uy * Paay + uz * Paaz)) * w - ua * ua * w3;
-        hab += (pab + (ux * Pabx + uy * Paby + uz * Pabz)) * w - ua * ub * w3;
-        hbb += (pbb + (ux * Pbbx + uy * Pbby + uz * Pbbz)) * w - ub * ub * w3;
+        const double dxz = tofrt_f3d_dot2(ux, nx, uz, nz);           /* -u.n_aa */
+        const double dn = fma(uy, ny, dxz);                          /* u.n */
+        const double dna = fma(ux, nz, -(uz * nx));                  /* u.n_a */
+        const double dnb = fma(uy, cb, -tofrt_f3d_dot2(ux, sasb, uz, casb));  /* u.n_b */
+        const double dnab = fma(uz, sasb, -(ux * casb));             /* u.n_ab */
+        const double ua = tofrt_f3d_dot2(ka, dn, f, dna);            /* u.P_a */
+        const double ub = tofrt_f3d_dot2(kb, dn, f, dnb);            /* u.P_b */
+        const double qaa = fma(kaa, dn, fma(2.0 * ka, dna, -(f * dxz)));
+        const double qab = fma(kab, dn, fma(ka, dnb, fma(kb, dna, f * dnab)));
+        const double qbb = fma(kbb, dn, fma(2.0 * kb, dnb, -(f * dn)));
+        tt = fma(r, ic, tt);
+        ga = fma(ua, w, ga);
+        gb = fma(ub, w, gb);
+        const double uaw3 = ua * w3;
+        haa += fma(paa + qaa, w, -(ua * uaw3));
+        hab += fma(pab + qab, w, -(ub * uaw3));
+        hbb += fma(pbb + qbb, w, -(ub * ub * w3));
     }
     *t = tt; g[0] = ga; g[1] = gb; H[0] = haa; H[1] = hab; H[2] = hbb;
 }

@@ -403,11 +403,23 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                 // on the rising side): then every sample up to mid certainly has that sign too.
                 const double sgn = pos0 ? sh : -sh;
                 const double ms_eff = pos0 ? -INFINITY : sh * m;
+                // "diff_mid certainly has the sign of diff_0", one fused operation per probe:
+                //   sgn (z - m x - b) > tol   <=   sgn z > fma(sgn m, x, sgn b + tol)
+                // (sgn = +-1: the products are exact; the two roundings are < tol/16, see docs/guided_search.md)
+                const double cm = sgn * m, cbt = sgn * b + tol;
+                const int zflip = sgn < 0.0 ? (int)0x80000000 : 0;
+                const int sflip = S.shape < 0 ? (int)0x80000000 : 0;  // uniform: sh * slope by a sign flip
+                const char *lens_b = reinterpret_cast<const char *>(s_lens);
+                const int slope_off = (int)(reinterpret_cast<const char *>(s_seg) - lens_b);  // uniform
                 int lo = 0, hi = N - 1;
                 for (int it = 0; it < S.log2n; ++it) {
                     const int mid = (lo + hi) >> 1;  // <= N-2 whenever hi - lo > 1
-                    const double dmid = line_diff(s_lens[mid], m, b);
-                    const bool cond = (sgn * dmid > tol) && (sh * s_seg[mid].x > ms_eff);
+                    const char *pa = lens_b + mid * 16;  // lens[mid]; the chord slope sits slope_off bytes further
+                    const double2 pm = *reinterpret_cast<const double2 *>(pa);
+                    const double slope = *reinterpret_cast<const double *>(pa + slope_off);
+                    const double zs = __hiloint2double(__double2hiint(pm.y) ^ zflip, __double2loint(pm.y));
+                    const double ss = __hiloint2double(__double2hiint(slope) ^ sflip, __double2loint(slope));
+                    const bool cond = (zs > fma(cm, pm.x, cbt)) && (ss > ms_eff);
                     const bool act = bracket && (hi - lo > 1);
                     lo = (act && cond) ? mid : lo;
                     hi = (act && !cond) ? mid : hi;
@@ -661,6 +673,13 @@ __device__ __forceinline__ float fsqrt_fast(float x)
 {
     float r;
     asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// flush-to-zero variant: no denormal pre-scaling around the MUFU (screening passes only)
+__device__ __forceinline__ float fsqrt_fast_ftz(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ int sincos_reduced_f(float x, float *s, float *c)
@@ -1090,6 +1109,9 @@ __global__ void __launch_bounds__(kFermatThreads) tofrt_fermat_kernel(DevSetup S
 // writes 2 KB runs.
 // =====================================================================================
 constexpr int kF3dThreads = 256;
+#ifndef TOFRT_F3D_MIN_BLOCKS
+#define TOFRT_F3D_MIN_BLOCKS 3
+#endif
 
 struct F3dArgs {
     const double *fx, *fy, *fz;  // [F] voxels
@@ -1117,7 +1139,7 @@ __global__ void tofrt_f3d_prepare_kernel(tofrt_surf3d S, F3dArgs A, float4 *smp)
     smp[(size_t)e * ns + s] = make_float4((float)P[0], (float)P[1], (float)P[2], (float)d1);
 }
 
-__global__ void __launch_bounds__(kF3dThreads) tofrt_fermat3d_kernel(tofrt_surf3d S, F3dArgs A)
+__global__ void __launch_bounds__(kF3dThreads, TOFRT_F3D_MIN_BLOCKS) tofrt_fermat3d_kernel(tofrt_surf3d S, F3dArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_smp = reinterpret_cast<float4 *>(smem_raw);
@@ -1152,7 +1174,7 @@ __global__ void __launch_bounds__(kF3dThreads) tofrt_fermat3d_kernel(tofrt_surf3
             for (int s = 0; s < ns; ++s) {
                 const float4 p = s_smp[s];
                 const float ux = p.x - gx, uy = p.y - gy, uz = p.z - gz;
-                const float t = fmaf(fsqrt_fast(fmaf(ux, ux, fmaf(uy, uy, uz * uz))), ic2, p.w);
+                const float t = fmaf(fsqrt_fast_ftz(fmaf(ux, ux, fmaf(uy, uy, uz * uz))), ic2, p.w);
                 const bool lt = t < best;
                 best = lt ? t : best;
                 kb = lt ? s : kb;

@@ -279,7 +279,7 @@ class TofEngine:
         return (tof, kmin, alpha) if with_alpha else (tof, kmin)
 
     # ---- 3-D two-point solve (extension, SURVEY row f4 / BASELINE config 5; parity unpinned) ----
-    def setup_fermat3d(self, ex, ey, n_side=17, ang=None):
+    def setup_fermat3d(self, ex, ey, n_side=9, ang=None):
         """Matrix-array elements (ex[e], ey[e], d) and the n_side x n_side grid of surface samples
         (default: np.linspace over the launch-angle range of setup()) for fermat3d_tof."""
         ex, ey = _f64(ex).ravel(), _f64(ey).ravel()

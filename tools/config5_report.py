@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--slabs", type=int, default=32, help="z-slabs (of 256) solved in total, split over the ranks")
-    ap.add_argument("--n-side", type=int, default=17)
+    ap.add_argument("--n-side", type=int, default=9)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--cpu", action="store_true", help="time the CPU twin on a small sample (rank 0)")
     ap.add_argument("--e2e", action="store_true", help="also time the host-buffer path on 2 slabs")
