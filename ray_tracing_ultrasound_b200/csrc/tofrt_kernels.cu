@@ -89,6 +89,10 @@ struct DevSetup {
     const double *x_rx;    // [E] as given
     const double *xs;      // [E_sorted] finite receivers, ascending
     const int *perm;       // [E_sorted] original index of xs[i]
+    // candidate lookup: bucket[c] = first i with xs[i] >= bx0 + (c-1)/binv (one cell of slack), nb cells
+    const int *bucket;
+    int nb;
+    double bx0, binv;
 };
 
 struct TableArgs {
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
     double *s_tof = s_xs + S.E_sorted;               // [kWarps][E] (absent when HG)
     int *s_perm = reinterpret_cast<int *>(s_tof + (HG ? (size_t)0 : (size_t)kWarps * E));
     int *s_khit = s_perm + S.E_sorted;               // [kWarps][E] (absent when HG)
+    int *s_bucket = s_khit + (HG ? (size_t)0 : (size_t)kWarps * E);  // [nb]
 
     // Stage the sampled surface once per CTA: two TMA bulk copies (lens samples, chords; 16-byte
     // aligned, multiples of 16 bytes) complete on one mbarrier while the threads load the small
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
         tma_bulk_g2s(s_seg, S.seg, seg_bytes, &s_bar);
     }
     for (int i = threadIdx.x; i < S.E_sorted; i += kThreads) { s_xs[i] = S.xs[i]; s_perm[i] = S.perm[i]; }
+    for (int i = threadIdx.x; i < S.nb; i += kThreads) s_bucket[i] = S.bucket[i];
     while (!mbar_try_wait(&s_bar, 0)) {}
     __syncthreads();
 
@@ -431,9 +437,12 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                     // the maximum of g, so no diff is >= 0.
                     // (lo == 0 was never tested against the slope: if g already falls from the first
                     // sample on, the maximum is g_0 -- so the bound below uses the larger of the two)
-                    const double ghi = sh * line_diff(s_lens[hi], m, b);
+                    // ("certainly negative" must be the loop's own probe: hi may have failed exactly that)
+                    const double2 ph = s_lens[hi];
+                    const double ghi = sh * line_diff(ph, m, b);
                     const double glo = sh * line_diff(s_lens[lo], m, b);
-                    if (ghi < -tol) { bracket = false; certain_none = true; edge = -fmax(ghi, glo) - tol; }
+                    const double zh = __hiloint2double(__double2hiint(ph.y) ^ zflip, __double2loint(ph.y));
+                    if (zh > fma(cm, ph.x, cbt)) { bracket = false; certain_none = true; edge = -fmax(ghi, glo) - tol; }
                 }
                 if (bracket) {
                     // exact classes from lo on (normally one step)
@@ -574,8 +583,18 @@ __global__ void __launch_bounds__(kThreads, TOFRT_MIN_BLOCKS) tofrt_table_kernel
                 bool mine = false;
                 if (cand) {
                     double tl = target_x - S.tol_max, th = target_x + S.tol_max;
-                    int l = 0, r = S.E_sorted;
-                    while (l < r) { int mid = (l + r) >> 1; if (s_xs[mid] < tl) l = mid + 1; else r = mid; }
+                    // first sorted receiver >= tl: a bucket lookup (start provably at or before it)
+                    // plus a short forward walk; binary search when no bucket table was built
+                    int l = 0;
+                    if (S.nb > 0) {
+                        const double cpos = (tl - S.bx0) * S.binv;
+                        const int c = cpos > 0.0 ? (cpos < (double)(S.nb - 1) ? (int)cpos : S.nb - 1) : 0;
+                        l = s_bucket[c];
+                        while (l < S.E_sorted && s_xs[l] < tl) ++l;
+                    } else {
+                        int r = S.E_sorted;
+                        while (l < r) { int mid = (l + r) >> 1; if (s_xs[mid] < tl) l = mid + 1; else r = mid; }
+                    }
                     lo = l;
                     hi = l;
                     while (hi < S.E_sorted && s_xs[hi] <= th) ++hi;
@@ -1289,7 +1308,7 @@ struct tofrt_ctx {
     size_t smem_f32 = 0;
     double *d_xrx = nullptr, *d_xs = nullptr, *d_sh = nullptr;
     int n_shooters = 1;
-    int *d_perm = nullptr, *d_bad = nullptr;
+    int *d_perm = nullptr, *d_bad = nullptr, *d_bucket = nullptr;
     unsigned long long *d_counter = nullptr;
     // host-buffer pipeline (tofrt_table_host)
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
@@ -1312,6 +1331,7 @@ struct tofrt_ctx {
     {
         cudaFree(d_alpha); cudaFree(d_zf); cudaFree(d_a); cudaFree(d_b); cudaFree(d_phi); cudaFree(d_leg1);
         cudaFree(d_lens); cudaFree(d_seg); cudaFree(d_f32); cudaFree(d_sh); cudaFree(d_xrx); cudaFree(d_xs); cudaFree(d_perm); cudaFree(d_bad);
+        cudaFree(d_bucket); d_bucket = nullptr;
         d_alpha = d_zf = d_a = d_b = d_phi = d_leg1 = d_xrx = d_xs = nullptr;
         d_lens = d_seg = nullptr; d_perm = d_bad = nullptr; d_f32 = nullptr; d_sh = nullptr;
     }
@@ -1428,8 +1448,30 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     S.rx_min = xs.empty() ? 1.0 : xs.front();
     S.rx_max = xs.empty() ? -1.0 : xs.back();
 
+    // bucket table for the candidate lookup of the table assembly: nb uniform cells over the finite
+    // receiver range (+- tol_max); bucket[c] = first sorted receiver >= start of cell c-1, so a lookup
+    // that is off by one cell through rounding still starts at or before the wanted receiver
+    std::vector<int> bucket;
+    S.nb = 0; S.bx0 = 0.0; S.binv = 0.0;
+#ifndef TOFRT_NO_BUCKET  /* tuning knob: binary search instead */
+    if (S.E_sorted >= 8) {
+        const double x0 = xs.front() - S.tol_max, range = (xs.back() + S.tol_max) - x0;
+        const int nb = std::min(4 * S.E_sorted, 8192);
+        const double cell = range / nb, binv = 1.0 / cell;
+        if (std::isfinite(range) && range > 0.0 && std::isfinite(binv) && cell > 0.0) {
+            bucket.resize(nb);
+            int i = 0;
+            for (int cidx = 0; cidx < nb; ++cidx) {
+                const double start = x0 + (cidx - 1) * cell;
+                while (i < S.E_sorted && xs[i] < start) ++i;
+                bucket[cidx] = i;
+            }
+            S.nb = nb; S.bx0 = x0; S.binv = binv;
+        }
+    }
+#endif
     const size_t smem_tables = (size_t)(S.Npad + K) * sizeof(double2) +
-                               (size_t)S.E_sorted * (sizeof(double) + sizeof(int)) + 16;
+                               (size_t)S.E_sorted * (sizeof(double) + sizeof(int)) + (size_t)S.nb * sizeof(int) + 16;
     size_t smem = smem_tables + (size_t)kWarps * E * (sizeof(double) + sizeof(int));
     S.hits_in_global = 0;
     if (smem > 227 * 1024) {  // many receivers: the per-warp first-hit state moves to the output rows
@@ -1465,6 +1507,9 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     S.lens = c->d_lens; S.seg = c->d_seg; S.a_pq = c->d_a; S.b_pq = c->d_b; S.phi_pq = c->d_phi; S.z_f = c->d_zf;
     S.x_sh = c->d_sh; S.z_sh = c->d_sh + NS;
     S.leg1 = c->d_leg1; S.x_rx = c->d_xrx; S.xs = c->d_xs; S.perm = c->d_perm;
+    CUDA_TRY(cudaMalloc(&c->d_bucket, sizeof(int) * std::max(1, S.nb)));
+    if (S.nb) CUDA_TRY(cudaMemcpy(c->d_bucket, bucket.data(), sizeof(int) * S.nb, cudaMemcpyHostToDevice));
+    S.bucket = c->d_bucket;
 
     tofrt_prepare_kernel<<<(S.Npad + 127) / 128, 128>>>(S, c->d_alpha, c->d_lens, c->d_a, c->d_b, c->d_phi,
                                                         c->d_leg1, c->d_bad);
