@@ -1162,12 +1162,14 @@ __global__ void __launch_bounds__(kF3dThreads, TOFRT_F3D_MIN_BLOCKS) tofrt_ferma
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_smp = reinterpret_cast<float4 *>(smem_raw);
-    __shared__ unsigned long long s_item;
     const int ns = A.n_side * A.n_side;
     const long long tiles = (A.F + kF3dThreads - 1) / kF3dThreads;
     const unsigned long long items = (unsigned long long)tiles * A.E;
     const float ic2 = (float)S.inv_c2;
     int cur_e = -1;
+    // Dynamic work counter, one (element, 256 voxels) item at a time.  (Dealing the items round-robin
+    // without the two barriers measured 4 % slower: the barrier keeps a CTA's warps in step.)
+    __shared__ unsigned long long s_item;
     for (;;) {
         __syncthreads();  // previous item done with s_smp / s_item
         if (threadIdx.x == 0) s_item = atomicAdd(A.counter, 1ull);
