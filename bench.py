@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=GRID_R, help="radii per GPU (default 1024; offsets stay 1024)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-3d", action="store_true", help="skip the 3-D two-point solve report (config 5 slice)")
     ap.add_argument("--gather", action="store_true",
                     help="after timing, all-gather the table shards over NCCL and check them (N > 1)")
     ap.add_argument("--search", default="guided", choices=["guided", "scan"],
@@ -346,6 +347,33 @@ def main():
     }
     del tof32, kh32, h64, h32, both, same_ray, dts
 
+    # ---- 3-D two-point solve (BASELINE config 5, extension -- parity unpinned), reported separately ----
+    f3d_info = None
+    if rank == 0 and not args.no_3d:
+        from ray_tracing_ultrasound_b200 import reference_setup as rs3
+        gm = (np.arange(32) - 15.5) * float(rs3.PITCH)                   # 32 x 32 matrix array
+        ex, ey = (v.ravel() for v in np.meshgrid(gm, gm, indexing="ij"))
+        eng.setup_fermat3d(ex, ey)                                       # default 9 x 9 surface grid
+        vz, vy, vx = (v.ravel() for v in np.meshgrid(np.linspace(0.0, 0.05, 256)[:4], np.linspace(-0.03, 0.03, 256),
+                                                     np.linspace(-0.03, 0.03, 256), indexing="ij"))
+        f3 = [torch.from_numpy(np.ascontiguousarray(v)).to(dev) for v in (vx, vy, vz)]
+        t3 = torch.empty((len(ex), len(vx)), dtype=torch.float64, device=dev)
+        eng.fermat3d_tof_cuda(*f3, out_tof=t3)
+        torch.cuda.synchronize()
+        e3 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e3[0].record()
+        for _ in range(3):
+            eng.fermat3d_tof_cuda(*f3, out_tof=t3)
+        e3[1].record()
+        torch.cuda.synchronize()
+        ms3 = e3[0].elapsed_time(e3[1]) / 3
+        f3d_info = {"value": len(ex) * len(vx) / (ms3 * 1e-3), "unit": "(element, voxel) pairs/s per GPU",
+                    "kernel_ms": ms3, "workload": "config 5 slice: 32x32 matrix array x 256x256x4 voxels of the 256^3 "
+                    "volume, lens of revolution, 9x9 surface grid + projected Newton",
+                    "all_finite": bool(torch.isfinite(t3).all()),
+                    "note": "no 3-D code in the reference: parity unpinned (oracles: NumPy/SciPy + bit-exact twin, tests/)"}
+        del t3, f3
+
     gather_info = None
     if args.gather and world > 1:
         from ray_tracing_ultrasound_b200 import sharding
@@ -413,6 +441,8 @@ def main():
             "roofline": roofline,
         }
         out["fp32"] = fp32_info
+        if f3d_info:
+            out["fermat3d"] = f3d_info
         if gather_info:
             out["all_gather"] = gather_info
         if not args.no_cpu:
