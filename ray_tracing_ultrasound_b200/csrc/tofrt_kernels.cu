@@ -563,9 +563,10 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
             // reflected (|sin| > 1 in main_rt.py:277), skip the rest of the arithmetic.
             double target_x = NAN;
             if (__any_sync(FULL, valid && ix == ix)) {
-                double alpha_i = tofrt_atan2(ix, iz);
+                // alpha_i = arctan2(ix, iz) is only ever used through sin/cos (main_rt.py:396-397):
+                // one fused elementary function, no angle
                 double sn, cs, h, dz, dx;
-                tofrt_sincos(alpha_i, &sn, &cs);
+                tofrt_sincos_atan2(ix, iz, &sn, &cs);
                 lens_point_t<FLAT>(S, sn, cs, &h, &dz, &dx);
                 // refraction(phi_l, (dz, dx), c2, c1), main_rt.py:272-278
                 double phi_slope = tofrt_atan2(dz, dx);

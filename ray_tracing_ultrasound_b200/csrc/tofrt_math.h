@@ -1,7 +1,7 @@
 /*
  * tofrt_math.h -- portable FP64 elementary functions of the TOF engine.
  *
- * sin, cos, tan, atan, atan2, asin built only from IEEE-754 operations that
+ * sin, cos, tan, atan, atan2, asin (and sincos-of-atan2) built only from IEEE-754 operations that
  * are correctly rounded on every target (+, -, *, /, sqrt, fma), so the very
  * same source gives bit-identical results when compiled
  *   - by nvcc for sm_100a (the product: csrc/tofrt_kernels.cu), and
@@ -17,7 +17,7 @@
  * polynomial coefficients live in constant memory on the device so that each
  * Horner step is a single DFMA with a c[bank][offset] operand.
  *
- * Accuracy (tests/test_math.py, against mpmath): sin, cos < 1.5 ulp; tan, atan,
+ * Accuracy (tests/test_math.py, against mpmath): sin, cos < 1.5 ulp; sincos-of-atan2 < 2.5 ulp; tan, atan,
  * atan2 < 2.5 ulp; asin < 3 ulp.  Domain of the trigonometric reduction:
  * |x| < 2^30 (angles in this engine never leave [-4 pi, 4 pi]); larger finite
  * arguments return NaN instead of a value with no correct digits.  sin/tan of
@@ -181,6 +181,21 @@ TOFRT_HD_BIG double tofrt_atan2(double y, double x)
 }
 
 TOFRT_HD double tofrt_atan(double x) { return tofrt_atan2(x, 1.0); }
+
+/* sin and cos of atan2(y, x) as one elementary function: (y, x) / hypot(x, y), no angle, no
+ * polynomial.  Used where the reference takes alpha = np.arctan2(x', z') and immediately evaluates
+ * sin(alpha), cos(alpha) (main_rt.py:396-397 -> :184, :203-204, :218-233).  < 2.5 ulp (one square
+ * root, one reciprocal, one product each), i.e. closer to the exact value than chaining a 2.5-ulp
+ * atan2 with 1.5-ulp sin/cos.  Domain: finite arguments of moderate size (lens coordinates);
+ * (0, +-0) gives (0, +-1) like the chained form, NaN propagates. */
+TOFRT_HD void tofrt_sincos_atan2(double y, double x, double *sn, double *cs)
+{
+    double r = sqrt(fma(x, x, y * y));
+    double inv = 1.0 / r;
+    int zero = (r == 0.0);
+    *sn = zero ? y : y * inv;
+    *cs = zero ? copysign(1.0, x) : x * inv;
+}
 
 /* asin(x) = atan2(x, sqrt((1 - x)(1 + x))); NaN for |x| > 1 (total internal
  * reflection in main_rt.py:277) */

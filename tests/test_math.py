@@ -45,12 +45,16 @@ def test_inverse_trig_accuracy(oracle_dm):
     assert _max_ulp(_eval(oracle_dm, 4, yy, xx), mp.atan2, [yy, xx]) < 2.0
     xs = np.concatenate([rng.uniform(-1, 1, 5000), 1 - 10.0 ** rng.uniform(-12, -1, 500)])
     assert _max_ulp(_eval(oracle_dm, 5, xs), mp.asin, [xs]) < 3.0
+    # the fused sin/cos of atan2(y, x): (y, x) / hypot -- closer to exact than chaining atan2 with sin/cos
+    yy, xx = rng.uniform(-0.1, 0.1, 6000), rng.uniform(-0.1, 0.1, 6000)
+    assert _max_ulp(_eval(oracle_dm, 6, yy, xx), lambda y, x: y / mp.sqrt(x * x + y * y), [yy, xx]) < 2.5
+    assert _max_ulp(_eval(oracle_dm, 7, yy, xx), lambda y, x: x / mp.sqrt(x * x + y * y), [yy, xx]) < 2.5
 
 
 def test_special_values(oracle_dm, oracle_libm):
     sp = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 1.0000001])
     y = np.array([1.0, -0.0, np.inf, -np.inf, 1.0, 0.0, -0.0, 1.0])
-    for fn in range(6):
+    for fn in range(6):   # (the fused pair 6, 7 is defined for finite lens coordinates only)
         a, b = _eval(oracle_dm, fn, sp, y), _eval(oracle_libm, fn, sp, y)
         assert np.array_equal(np.isnan(a), np.isnan(b)), fn
         ok = ~np.isnan(a)
