@@ -75,4 +75,22 @@ for i in range(n4):
 out["random_setups_vs_twin_oracle"] = {"setups": n4, "geometries_per_setup": per, "rays": rays, "mismatches": bad,
                                        "varied": "c1, c2, l0, h0, K in [64, 2000), 16-256 elements, pitch, aperture, shooter, rtol/atol, search mode",
                                        "seconds": round(time.time() - t0, 1)}
+# (4) 3-D two-point solve (extension) vs its CPU twin: bit-identical wherever the start sample agrees
+x65, z65 = rs.transducer()
+eng.setup(rs.launch_angles(), rs.focus_line(), x65[32], z65[32], x65)
+n5 = int(os.environ.get("FUZZ_3D_VOXELS", "40000"))
+r5 = np.random.default_rng(77)
+gm = (np.arange(32) - 15.5) * float(rs.PITCH)
+ex, ey = (v.ravel()[::4] for v in np.meshgrid(gm, gm, indexing="ij"))      # 256 of the 32 x 32 elements
+eng.setup_fermat3d(ex, ey)
+fx, fy, fz = r5.uniform(-0.03, 0.03, n5), r5.uniform(-0.03, 0.03, n5), r5.uniform(0.0, 0.05, n5)
+t0 = time.time()
+tg, kg, abg = eng.fermat3d_tof(fx, fy, fz, with_angles=True)
+tt, kt, abt, ev, gap = o.fermat3d(o.params(), eng.f3_ang, ex, ey, float(rs.D), fx, fy, fz)
+same = kg == kt
+out["fermat3d_vs_twin"] = {"pairs": int(tg.size), "same_start_sample_frac": float(same.mean()),
+                           "bit_identical_where_same_start": bool((tg[same] == tt[same]).all() and (abg[same] == abt[same]).all()),
+                           "max_abs_dt_other_start_s": float(np.abs(tg - tt)[~same].max(initial=0.0)),
+                           "max_grid_gap_other_start_s": float(gap[~same].max(initial=0.0)),
+                           "max_newton_evaluations": int(ev.max()), "seconds": round(time.time() - t0, 1)}
 print(json.dumps(out, indent=1))

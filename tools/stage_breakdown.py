@@ -24,7 +24,7 @@ LIB = os.path.join(ROOT, "ray_tracing_ultrasound_b200", "libtofrt.so")
 MARKERS = {
     "tofrt_table_kernel": [
         ("tofrt_table_kernel(DevSetup S, TableArgs T)", "kernel prologue (staging, TMA)"),
-        ("unsigned long long g64 = 0;", "per-geometry setup"),
+        ("__shared__ unsigned long long s_base;", "per-geometry setup (work fetch, state reset)"),
         ("// ---- main_rt.py:351-364 pipe intersection", "stage 2a: pipe intersection (main_rt.py:351-364)"),
         ("// ---- main_rt.py:367-376 reflection", "stage 2b: reflection, atan, tan (main_rt.py:367-376)"),
         ("// ---- main_rt.py:78-99 first sign change", "return-path search (main_rt.py:78-99)"),
