@@ -811,15 +811,11 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
     int *w_khit = s_khit + (size_t)warp * E;
     const int nchunks = (K + 31) >> 5;
     const unsigned FULL = 0xffffffffu;
-    __shared__ unsigned long long s_base;  // CTA-level work fetch, as in tofrt_table_kernel
-    const unsigned long long total = (unsigned long long)T.G * (unsigned long long)T.s_count;
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_base = atomicAdd(T.counter, (unsigned long long)kWarps);
-        __syncthreads();
-        if (s_base >= total) break;
-        const unsigned long long g64 = s_base + warp;
-        if (g64 >= total) continue;
+    for (;;) {  // per-warp work fetch (the CTA-level fetch of the FP64 kernel measured 5 % slower here)
+        unsigned long long g64 = 0;
+        if (lane == 0) g64 = atomicAdd(T.counter, 1ull);
+        g64 = __shfl_sync(FULL, g64, 0);
+        if (g64 >= (unsigned long long)T.G * (unsigned long long)T.s_count) break;
         const long long w = (long long)g64;
         const long long g = w % T.G;
         const size_t sk = (size_t)(T.s_begin + w / T.G) * K;
@@ -919,9 +915,15 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
             }
             float target_x = NAN;
             if (__any_sync(FULL, valid && ix == ix)) {
-                float alpha_i = atan2_f(ix, iz);
+                // sin/cos of atan2(ix, iz) without the angle, as in the FP64 kernel
                 float sn, cs;
-                sincos_f(alpha_i, &sn, &cs);
+                {
+                    const float r2 = fmaf(ix, ix, iz * iz);
+                    float inv;
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r2));
+                    sn = ix * inv;
+                    cs = iz * inv;
+                }
                 float hh, dh;
                 if (S.surface == 0) {
                     float B = S.twod * cs - S.K2;
