@@ -43,3 +43,28 @@ def gather_table(tof_shard, k_hit_shard, G, group=None):
         return torch.cat([out[r * max_rows: r * max_rows + (hi - lo)] for r, (lo, hi) in enumerate(rows)])
 
     return gather(tof_shard), gather(k_hit_shard)
+
+
+# ---- the two-point solves: element-major tables [E][F], focal points / voxels sharded ----
+def shard_points(points, world_size, rank):
+    """Contiguous slice of each coordinate array (fx, fz) or (fx, fy, fz) for this rank."""
+    lo, hi = shard_bounds(len(points[0]), world_size, rank)
+    return tuple(np.ascontiguousarray(p[lo:hi]) for p in points)
+
+
+def gather_point_table(shard, F, group=None):
+    """All-gather the [E][F_r] shards of a two-point table (tofrt_fermat*_dev output) into [E][F] on
+    every rank.  The table is element-major, so the shards interleave: gather the transposed,
+    point-major blocks (contiguous per rank) and transpose back."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    E = shard.shape[0]
+    cols = [shard_bounds(F, world, r) for r in range(world)]
+    max_cols = max(hi - lo for lo, hi in cols)
+    pad = torch.zeros((max_cols, E), dtype=shard.dtype, device=shard.device)
+    pad[: shard.shape[1]] = shard.t()
+    out = torch.empty((world * max_cols, E), dtype=shard.dtype, device=shard.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    full = torch.cat([out[r * max_cols: r * max_cols + (hi - lo)] for r, (lo, hi) in enumerate(cols)])
+    return full.t().contiguous()

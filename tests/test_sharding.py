@@ -59,3 +59,39 @@ def test_shard_gather_roundtrip_gloo_world2(G):
         pr.join(120)
         assert pr.exitcode == 0
     assert out.get() is True
+
+
+def _worker3d(rank, world, port, F, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import Oracle
+    o = Oracle(device_math=True)
+    p = o.params()
+    rng = np.random.default_rng(5)
+    ang = np.linspace(-rs.ALPHA_MAX, rs.ALPHA_MAX, 9)
+    ex, ey = rng.uniform(-0.009, 0.009, 6), rng.uniform(-0.009, 0.009, 6)
+    pts = (rng.uniform(-0.03, 0.03, F), rng.uniform(-0.03, 0.03, F), rng.uniform(0.0, 0.05, F))
+    mine = sharding.shard_points(pts, world, rank)
+    tof = o.fermat3d(p, ang, ex, ey, float(rs.D), *mine)[0]
+    full = sharding.gather_point_table(torch.from_numpy(tof), F)
+    if rank == 0:
+        ref = o.fermat3d(p, ang, ex, ey, float(rs.D), *pts)[0]
+        out.put(bool(np.array_equal(full.numpy(), ref)) and full.shape == (6, F))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("F", [10, 9])
+def test_voxel_shards_gather_roundtrip_gloo_world2(F):
+    """The two-point tables are element-major [E][F]: voxel shards interleave on gathering."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    out = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker3d, args=(r, 2, port, F, out)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(120)
+        assert pr.exitcode == 0
+    assert out.get() is True
