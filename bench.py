@@ -322,6 +322,28 @@ def main():
     del tof_o, kh_o
     eng.set_search(args.search)
 
+    # ---- the reference-order math mode (TOFRT_MATH_ANGLE) beside the default vector form ----
+    eng.set_math("angle")
+    tof_a = torch.empty_like(tof_d)
+    kh_a = torch.empty_like(kh_d)
+    eng.tof_table_cuda(r_d, o_d, out_tof=tof_a, out_k_hit=kh_a)
+    barrier()
+    ea = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ea[0].record()
+    for _ in range(2):
+        eng.tof_table_cuda(r_d, o_d, out_tof=tof_a, out_k_hit=kh_a)
+    ea[1].record()
+    barrier()
+    both_a = (kh_a >= 0) & (kh_d >= 0)
+    math_info = {"default": "vector", "angle_kernel_ms": ea[0].elapsed_time(ea[1]) / 2,
+                 "k_hit_mismatches_vs_angle": int((kh_a != kh_d).sum()),
+                 "max_abs_dt_vs_angle_s": float((tof_a - tof_d)[both_a].abs().max()),
+                 "note": "TOFRT_OPT_MATH: 'vector' evaluates the reflection / refraction laws of the return path from direction "
+                         "cosines (csrc/tofrt_raymath.h), 'angle' keeps the reference's angle bookkeeping and operation order; "
+                         "both are bit-identical to their CPU twin and pass the same parity tests"}
+    del tof_a, kh_a, both_a
+    eng.set_math("vector")
+
     # ---- FP32 mode, reported separately (north_star): time and measured error vs FP64 ----
     tof32 = torch.empty((G, E), dtype=torch.float32, device=dev)
     kh32 = torch.empty((G, E), dtype=torch.int32, device=dev)
@@ -442,6 +464,7 @@ def main():
             "gpu_launches": args.steps * 1,
             "roofline": roofline,
         }
+        out["math_modes"] = math_info
         out["fp32"] = fp32_info
         if f3d_info:
             out["fermat3d"] = f3d_info

@@ -108,12 +108,30 @@ int tofrt_setup_shooters(tofrt_ctx *ctx, const tofrt_params *params, const doubl
 #define TOFRT_OPT_SURFACE 2
 #define TOFRT_SURFACE_LENS 0
 #define TOFRT_SURFACE_FLAT 1
+/* TOFRT_OPT_MATH: how the two interface laws of the return path -- reflection on the pipe
+ * (main_rt.py:283-292, 367-375) and refraction back into the lens (main_rt.py:267-280, 396-401) -- are
+ * evaluated.  TOFRT_MATH_ANGLE: the reference's own bookkeeping, every direction an angle
+ * (atan / tan, atan2 / sin / asin / tan), in the reference's operation order.  TOFRT_MATH_VECTOR: the
+ * same quantities from direction cosines by the addition theorems (csrc/tofrt_raymath.h): no angle is
+ * formed, two square roots and three divisions replace seven elementary-function calls per ray, fewer
+ * roundings; results agree with the angle form to ~1e-15 relative, i.e. identical hit decisions and
+ * travel times within 1e-17 s (tests), and the first-sign-change index differs only where it is
+ * rounding noise (the reference's 12 degenerate fixture geometries).  Both forms are bit-identical
+ * to their CPU twin.  Default: TOFRT_MATH_VECTOR (24 % faster; the whole GPU parity suite runs in both
+ * modes).  May be changed at any time after tofrt_create. */
+#define TOFRT_OPT_MATH 3
+#define TOFRT_MATH_ANGLE 0
+#define TOFRT_MATH_VECTOR 1
+#ifndef TOFRT_MATH_DEFAULT
+#define TOFRT_MATH_DEFAULT TOFRT_MATH_VECTOR
+#endif
 int tofrt_set_option(tofrt_ctx *ctx, int option, int value);
 
 /* Facts about the current setup: TOFRT_INFO_SHAPE -> +1 concave / -1 convex /
  * 0 neither (guided search disabled); TOFRT_INFO_SEARCH -> current search mode. */
 #define TOFRT_INFO_SHAPE 1
 #define TOFRT_INFO_SEARCH 2
+#define TOFRT_INFO_MATH 3
 int tofrt_get_info(tofrt_ctx *ctx, int what);
 
 /* Search statistics of the most recent table call on this context (synchronises):

@@ -61,6 +61,10 @@ class Oracle:
         """Extension: flat interface z = h0 instead of the reference's lens (process-wide switch)."""
         self.lib.tofo_set_surface(ctypes.c_int(1 if flat else 0))
 
+    def set_math(self, vector):
+        """Twin build: the product's vector form of the return-path interface laws (process-wide switch)."""
+        self.lib.tofo_set_math(ctypes.c_int(1 if vector else 0))
+
     def max_threads(self):
         return int(self.lib.tofo_max_threads())
 

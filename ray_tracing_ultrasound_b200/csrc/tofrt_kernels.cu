@@ -43,6 +43,7 @@
 #include "../../include/tofrt.h"
 #include "tofrt_math.h"
 #include "tofrt_fermat3d.h"
+#include "tofrt_raymath.h"
 
 #define HALF_PI 1.5707963267948966 /* np.pi / 2 */
 
@@ -86,6 +87,7 @@ struct DevSetup {
     int hits_in_global;  // 1: E too large for the per-warp shared-memory first-hit state -> keep it in the output rows
     int shape;      // +1: sampled lens strictly concave in x, -1: strictly convex, 0: neither (no guided search)
     int guided;     // search mode: 1 = guided (bracketed) search, 0 = the reference's literal O(N) scan
+    int vector_math;  // 1: return-path interface laws in vector form (tofrt_raymath.h), 0: the reference's angles
     int log2n;      // ceil(log2(K)) bisection steps
     double X, Z;    // max |x_p|, max |z_p|  (rounding-error bound of a diff)
     int surface;    // 0: the reference's constant-TOF lens h(alpha); 1: flat interface z = h0 (extension)
@@ -94,6 +96,7 @@ struct DevSetup {
     const double2 *lens;   // [Npad] (x_p, z_p), padded with copies of the last sample
     const double2 *seg;    // [K-1] chord (m_seg, b_seg) of main_rt.py:127-128
     const double *a_pq, *b_pq, *phi_pq, *z_f, *leg1;  // [K]
+    const double *cpq, *spq;  // [K] cos / sin of phi_pq (vector form of the interface laws)
     const double *x_rx;    // [E] as given
     const double *xs;      // [E_sorted] finite receivers, ascending
     const int *perm;       // [E_sorted] original index of xs[i]
@@ -210,7 +213,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
 
 // ---- prepare kernel: main_rt.py:338-349 for every launch angle ----------------
 __global__ void tofrt_prepare_kernel(DevSetup S, const double *alpha, double2 *lens, double *a_pq,
-                                     double *b_pq, double *phi_pq, double *leg1, int *bad)
+                                     double *b_pq, double *phi_pq, double *leg1, double *cpq, double *spq, int *bad)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= S.Npad) return;
@@ -232,6 +235,7 @@ __global__ void tofrt_prepare_kernel(DevSetup S, const double *alpha, double2 *l
         a_pq[o] = a;
         b_pq[o] = z_p - a * x_p;
         phi_pq[o] = phi;
+        tofrt_sincos(phi, &spq[o], &cpq[o]);
         leg1[o] = dist2d(x_sh, z_sh, x_p, z_p) / S.c1;
     }
 }
@@ -291,7 +295,8 @@ __device__ __forceinline__ void chord_intersection(const double2 *lens, const do
 // HG: first-hit state in the output rows (global memory) instead of warp-private shared memory
 // GUIDED: compile the guided search (its rare fallback is then a plain per-ray exact scan) or the
 // warp-wide literal scan -- two lean instruction streams instead of one kernel carrying both.
-template <bool HG, bool GUIDED, bool FLAT>
+// VEC: the two return-path interface laws in vector form (tofrt_raymath.h) instead of the reference's angles
+template <bool HG, bool GUIDED, bool FLAT, bool VEC>
 __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_BLOCKS)
     tofrt_table_kernel(DevSetup S, TableArgs T)
 {
@@ -367,7 +372,9 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
             const bool valid = k < K;
             const int kk = valid ? k : K - 1;
             // per-ray constants of the shot: one coalesced, L1-resident load per 32 rays
-            const double a_pq = __ldg(S.a_pq + sk + kk), b_pq = __ldg(S.b_pq + sk + kk), phi_pq = __ldg(S.phi_pq + sk + kk);
+            const double a_pq = __ldg(S.a_pq + sk + kk), b_pq = __ldg(S.b_pq + sk + kk);
+            const double phi_pq = VEC ? 0.0 : __ldg(S.phi_pq + sk + kk);
+            const double cpq = VEC ? __ldg(S.cpq + sk + kk) : 0.0, spq = VEC ? __ldg(S.spq + sk + kk) : 0.0;
             const double z_f = __ldg(S.z_f + kk);
 
             // ---- main_rt.py:351-364 pipe intersection, upper root ----
@@ -385,8 +392,12 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 z_q = up ? z_q1 : z_q2;
             }
             // ---- main_rt.py:367-376 reflection on the pipe ----
-            double phi_l, m, b;
-            {
+            double phi_l = 0.0, cl = 0.0, sl = 0.0, m, b;  // reflected direction: angle, or r^2 (cos, sin)
+            if (VEC) {
+                tofrt_vec_reflect(x_q, rsq, cpq, spq, &cl, &sl);
+                m = sl / cl;
+                b = z_q - m * x_q;
+            } else {
                 double slope = -x_q / sqrt(rsq - x_q * x_q);  // dzdx_pipe ignores the offset (:237-238)
                 double phi_slope = tofrt_atan(slope);
                 double theta_1 = phi_pq - (phi_slope + HALF_PI);
@@ -569,13 +580,21 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 tofrt_sincos_atan2(ix, iz, &sn, &cs);
                 lens_point_t<FLAT>(S, sn, cs, &h, &dz, &dx);
                 // refraction(phi_l, (dz, dx), c2, c1), main_rt.py:272-278
-                double phi_slope = tofrt_atan2(dz, dx);
-                double theta_1 = phi_l - (phi_slope + HALF_PI);
-                double s_arg = S.c1_over_c2 * tofrt_sin(theta_1);
+                double phi_slope = 0.0, s_arg;
+                if (VEC) s_arg = S.c1_over_c2 * tofrt_vec_sin_theta1(cl, sl, rsq, dz, dx);
+                else {
+                    phi_slope = tofrt_atan2(dz, dx);
+                    double theta_1 = phi_l - (phi_slope + HALF_PI);
+                    s_arg = S.c1_over_c2 * tofrt_sin(theta_1);
+                }
                 if (__any_sync(FULL, valid && fabs(s_arg) <= 1.0)) {
-                    double theta_2 = tofrt_asin(s_arg);
-                    double phi_last = phi_slope - HALF_PI + theta_2;
-                    double a_i = tofrt_tan(phi_last);
+                    double a_i;
+                    if (VEC) a_i = tofrt_vec_refract_slope(s_arg, dz, dx);
+                    else {
+                        double theta_2 = tofrt_asin(s_arg);
+                        double phi_last = phi_slope - HALF_PI + theta_2;
+                        a_i = tofrt_tan(phi_last);
+                    }
                     double b_i = iz - a_i * ix;
                     target_x = (z_f - b_i) / a_i;
                 }
@@ -1309,6 +1328,19 @@ int fail(int code, const std::string &msg)
     return code;
 }
 
+typedef void (*table_kernel_t)(DevSetup, TableArgs);
+// the instantiation for (first-hit state in global memory, guided search, flat surface, vector math)
+table_kernel_t pick_table_kernel(bool hg, bool guided, bool flat, bool vec)
+{
+    if (flat) return vec ? tofrt_table_kernel<false, false, true, true> : tofrt_table_kernel<false, false, true, false>;
+    if (hg) {
+        if (guided) return vec ? tofrt_table_kernel<true, true, false, true> : tofrt_table_kernel<true, true, false, false>;
+        return vec ? tofrt_table_kernel<true, false, false, true> : tofrt_table_kernel<true, false, false, false>;
+    }
+    if (guided) return vec ? tofrt_table_kernel<false, true, false, true> : tofrt_table_kernel<false, true, false, false>;
+    return vec ? tofrt_table_kernel<false, false, false, true> : tofrt_table_kernel<false, false, false, false>;
+}
+
 #define CUDA_TRY(expr)                                                                        \
     do {                                                                                      \
         cudaError_t e_ = (expr);                                                              \
@@ -1329,9 +1361,11 @@ struct tofrt_ctx {
     int ctas_per_sm = 1;
     // device buffers owned by the context
     double *d_alpha = nullptr, *d_zf = nullptr, *d_a = nullptr, *d_b = nullptr, *d_phi = nullptr, *d_leg1 = nullptr;
+    double *d_cs = nullptr;   // cos / sin of phi_pq, [2][S*K]
     double2 *d_lens = nullptr, *d_seg = nullptr;
     int opt_guided = 1;
     int opt_surface = 0;
+    int opt_vector = TOFRT_MATH_DEFAULT;
     float *d_f32 = nullptr;   // FP32 copies of the tables (FP32 mode)
     DevSetupF SF{};
     size_t smem_f32 = 0;
@@ -1361,6 +1395,7 @@ struct tofrt_ctx {
         cudaFree(d_alpha); cudaFree(d_zf); cudaFree(d_a); cudaFree(d_b); cudaFree(d_phi); cudaFree(d_leg1);
         cudaFree(d_lens); cudaFree(d_seg); cudaFree(d_f32); cudaFree(d_sh); cudaFree(d_xrx); cudaFree(d_xs); cudaFree(d_perm); cudaFree(d_bad);
         cudaFree(d_bucket); d_bucket = nullptr;
+        cudaFree(d_cs); d_cs = nullptr;
         d_alpha = d_zf = d_a = d_b = d_phi = d_leg1 = d_xrx = d_xs = nullptr;
         d_lens = d_seg = nullptr; d_perm = d_bad = nullptr; d_f32 = nullptr; d_sh = nullptr;
     }
@@ -1517,6 +1552,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     CUDA_TRY(cudaMalloc(&c->d_b, sizeof(double) * K * NS));
     CUDA_TRY(cudaMalloc(&c->d_phi, sizeof(double) * K * NS));
     CUDA_TRY(cudaMalloc(&c->d_leg1, sizeof(double) * K * NS));
+    CUDA_TRY(cudaMalloc(&c->d_cs, sizeof(double) * 2 * K * NS));
     CUDA_TRY(cudaMalloc(&c->d_lens, sizeof(double2) * S.Npad));
     CUDA_TRY(cudaMalloc(&c->d_seg, sizeof(double2) * K));
     CUDA_TRY(cudaMemset(c->d_seg, 0, sizeof(double2) * K));  // entry K-1 is padding (TMA copies K entries)
@@ -1536,13 +1572,14 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     CUDA_TRY(cudaMemset(c->d_bad, 0, sizeof(int)));
     S.lens = c->d_lens; S.seg = c->d_seg; S.a_pq = c->d_a; S.b_pq = c->d_b; S.phi_pq = c->d_phi; S.z_f = c->d_zf;
     S.x_sh = c->d_sh; S.z_sh = c->d_sh + NS;
+    S.cpq = c->d_cs; S.spq = c->d_cs + (size_t)K * NS;
     S.leg1 = c->d_leg1; S.x_rx = c->d_xrx; S.xs = c->d_xs; S.perm = c->d_perm;
     CUDA_TRY(cudaMalloc(&c->d_bucket, sizeof(int) * std::max(1, S.nb)));
     if (S.nb) CUDA_TRY(cudaMemcpy(c->d_bucket, bucket.data(), sizeof(int) * S.nb, cudaMemcpyHostToDevice));
     S.bucket = c->d_bucket;
 
     tofrt_prepare_kernel<<<(S.Npad + 127) / 128, 128>>>(S, c->d_alpha, c->d_lens, c->d_a, c->d_b, c->d_phi,
-                                                        c->d_leg1, c->d_bad);
+                                                        c->d_leg1, c->d_cs, c->d_cs + (size_t)K * NS, c->d_bad);
     CUDA_TRY(cudaGetLastError());
     tofrt_chord_kernel<<<(K + 127) / 128, 128>>>(K, c->d_lens, c->d_seg);
     CUDA_TRY(cudaGetLastError());
@@ -1576,6 +1613,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
         S.log2n = lg;  // ceil-halving an interval of length K-1 <= 2^lg reaches length 1 in lg steps
     }
     S.guided = c->opt_guided;
+    S.vector_math = c->opt_vector;
     // ---- FP32 mode: the same tables rounded to float ----
     {
         const int Es = std::max(1, S.E_sorted);
@@ -1615,18 +1653,14 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
 
     if (S.surface != 0 && S.hits_in_global)
         return fail(TOFRT_E_TOOLARGE, "tofrt_setup: the flat-interface extension supports the shared-memory receiver budget only");
-    if (S.surface != 0) {
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    } else if (S.hits_in_global) {
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_guided));
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_guided));
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    const bool flat = S.surface != 0, hg = S.hits_in_global != 0;
+    for (int vec = 0; vec < 2; ++vec)
+        for (int gd = 0; gd < (flat ? 1 : 2); ++gd)
+            CUDA_TRY(cudaFuncSetAttribute(pick_table_kernel(hg, gd != 0, flat, vec != 0),
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(gd ? smem_guided : smem)));
     int occ = 1;
-    if (S.hits_in_global) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<true, true, false>, kThreadsGuided, smem_guided));
-    else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_table_kernel<false, true, false>, kThreadsGuided, smem_guided));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_table_kernel(hg, !flat, flat, c->opt_vector != 0),
+                                                             flat ? kThreads : kThreadsGuided, flat ? smem : smem_guided));
     c->ctas_per_sm = std::max(1, occ);
     c->smem_guided = smem_guided;
     c->S = S; c->K = K; c->E = E; c->smem = smem; c->n_shooters = NS; c->params_d = p->d;
@@ -1642,6 +1676,13 @@ int tofrt_set_option(tofrt_ctx *c, int option, int value)
             return fail(TOFRT_E_BADARG, "tofrt_set_option: bad search mode");
         c->opt_guided = value;
         c->S.guided = value;
+        return TOFRT_OK;
+    }
+    if (option == TOFRT_OPT_MATH) {
+        if (value != TOFRT_MATH_ANGLE && value != TOFRT_MATH_VECTOR)
+            return fail(TOFRT_E_BADARG, "tofrt_set_option: bad math mode");
+        c->opt_vector = value;
+        c->S.vector_math = value;
         return TOFRT_OK;
     }
     if (option == TOFRT_OPT_SURFACE) {
@@ -1668,6 +1709,7 @@ int tofrt_get_info(tofrt_ctx *c, int what)
     switch (what) {
     case TOFRT_INFO_SHAPE: return c->ready ? c->S.shape : 0;
     case TOFRT_INFO_SEARCH: return c->opt_guided;
+    case TOFRT_INFO_MATH: return c->opt_vector;
     default: return TOFRT_E_BADARG;
     }
 }
@@ -1707,15 +1749,9 @@ static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_
     const int threads = guided ? kThreadsGuided : kThreads, wpc = threads / 32;
     const size_t smem = guided ? c->smem_guided : c->smem;
     int grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, (warps_needed + wpc - 1) / wpc);
-    if (c->S.surface != 0) {  // flat interface (extension): a plane has no strict curvature, literal scan only
-        tofrt_table_kernel<false, false, true><<<grid, threads, smem, st>>>(c->S, T);
-    } else if (c->S.hits_in_global) {
-        if (guided) tofrt_table_kernel<true, true, false><<<grid, threads, smem, st>>>(c->S, T);
-        else tofrt_table_kernel<true, false, false><<<grid, threads, smem, st>>>(c->S, T);
-    } else {
-        if (guided) tofrt_table_kernel<false, true, false><<<grid, threads, smem, st>>>(c->S, T);
-        else tofrt_table_kernel<false, false, false><<<grid, threads, smem, st>>>(c->S, T);
-    }
+    // (flat interface, extension: a plane has no strict curvature, so `guided` is false there: literal scan only)
+    pick_table_kernel(c->S.hits_in_global != 0, guided, c->S.surface != 0, c->S.vector_math != 0)
+        <<<grid, threads, smem, st>>>(c->S, T);
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
 }
@@ -2225,8 +2261,7 @@ int tofrt_kernel_info(tofrt_ctx *c, int *grid, int *block, int *smem_bytes, int 
     if (!c) return fail(TOFRT_E_BADARG, "tofrt_kernel_info: ctx is NULL");
     const bool guided = c->S.guided && c->S.shape != 0 && c->S.surface == 0;
     cudaFuncAttributes fa{};
-    if (guided) CUDA_TRY(cudaFuncGetAttributes(&fa, tofrt_table_kernel<false, true, false>));
-    else CUDA_TRY(cudaFuncGetAttributes(&fa, tofrt_table_kernel<false, false, false>));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, pick_table_kernel(false, guided, false, c->S.vector_math != 0)));
     if (grid) *grid = c->sm_count * c->ctas_per_sm;
     if (block) *block = guided ? kThreadsGuided : kThreads;
     if (smem_bytes) *smem_bytes = (int)(guided ? c->smem_guided : c->smem);

@@ -102,6 +102,16 @@ class TofEngine:
         _capi.check(self._lib.tofrt_set_option(self._ctx, 2, {"lens": 0, "flat": 1}[kind]))
         return self
 
+    def set_math(self, mode):
+        """'angle' (the reference's angle bookkeeping, in its operation order) or 'vector' (the same interface
+        laws from direction cosines, csrc/tofrt_raymath.h: faster, same decisions); see TOFRT_OPT_MATH."""
+        _capi.check(self._lib.tofrt_set_option(self._ctx, 3, {"angle": 0, "vector": 1}[mode]))
+        return self
+
+    @property
+    def math_mode(self):
+        return "vector" if self._lib.tofrt_get_info(self._ctx, 3) == 1 else "angle"
+
     def set_search(self, mode):
         """'guided' (default) or 'scan' (the reference's literal O(N) search); same results."""
         value = {"scan": 0, "guided": 1}[mode]

@@ -39,3 +39,15 @@ def engine():
     if _build.is_stale():
         _build.build()
     return TofEngine(0)
+
+
+@pytest.fixture(params=["angle", "vector"])
+def math_mode(request, engine, oracle_dm):
+    """Runs a GPU test once per TOFRT_OPT_MATH mode, with the oracle twin switched alike
+    (modules opt in with pytest.mark.usefixtures("math_mode"))."""
+    default = engine.math_mode
+    engine.set_math(request.param)
+    oracle_dm.set_math(request.param == "vector")
+    yield request.param
+    engine.set_math(default)
+    oracle_dm.set_math(False)

@@ -7,7 +7,7 @@ import pytest
 from ray_tracing_ultrasound_b200 import reference_setup as rs
 from fermat_oracle import Lens, fermat_table
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("math_mode")]
 
 
 @pytest.fixture()

@@ -10,7 +10,7 @@ import pytest
 
 from ray_tracing_ultrasound_b200 import reference_setup as rs
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("math_mode")]
 
 TOF_TOL = 1e-12  # seconds, north_star
 NOISE_FLOOR = 1e-13

@@ -7,7 +7,7 @@ import pytest
 
 from ray_tracing_ultrasound_b200 import reference_setup as rs
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("math_mode")]
 
 
 def numpy_rule(x, z, m, b):

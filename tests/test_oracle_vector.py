@@ -1,0 +1,68 @@
+"""CPU: the vector form of the return-path interface laws (csrc/tofrt_raymath.h, TOFRT_MATH_VECTOR),
+evaluated through the oracle's device-math twin, against the angle form (the reference's operation order)
+and against the independent libm oracle: same hit decisions, same first-sign-change indices wherever the
+decision is not rounding noise, travel times far inside 1e-12 s, same NaN pattern."""
+import numpy as np
+
+from ray_tracing_ultrasound_b200 import reference_setup as rs
+
+
+def _tables(oracle_dm, oracle_libm, radii, offsets, n_alpha=905):
+    x_a, z_a = rs.transducer()
+    alpha, zf = rs.launch_angles(n_alpha), rs.focus_line(n_alpha)
+    p = oracle_dm.params()
+    args = (p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a)
+    try:
+        oracle_dm.set_math(True)
+        vec = oracle_dm.table(*args, want_idx=True)
+    finally:
+        oracle_dm.set_math(False)
+    return vec, oracle_dm.table(*args, want_idx=True), oracle_libm.table(*args, want_idx=True)
+
+
+def test_vector_form_on_the_fixture_sweep(oracle_dm, oracle_libm, golden):
+    radii, offsets = rs.sweep_grid()
+    (t1, k1, i1), (t0, k0, i0), (tl, kl, il) = _tables(oracle_dm, oracle_libm, radii, offsets)
+    assert np.array_equal(k1, k0) and np.array_equal(k1, kl)
+    hit = k1 >= 0
+    assert np.abs(t1 - t0)[hit].max() < 1e-17 and np.abs(t1 - tl)[hit].max() < 1e-17
+    # the reference's own fixture
+    db = golden["database_2"]
+    assert np.array_equal(hit.T, db["hitted"].reshape(210, 65))
+    assert np.abs(t1.T - db["tof_total"].reshape(210, 65)).max() < 1e-12
+    # the index differs only in the 12 degenerate geometries (the ray retraces its path through a lens sample)
+    degenerate = (offsets == 0) | ((radii == 0.01) & (np.abs(offsets) == 0.01))
+    assert degenerate.sum() == 12
+    assert np.array_equal(i1[~degenerate], i0[~degenerate]) and np.array_equal(i1[~degenerate], il[~degenerate])
+    sw = golden["sweep"]     # the unmodified reference: identical wherever its own decision exceeds the noise floor
+    ridx = sw["idx"].astype(np.int32)
+    gi = np.where(i1 < -1, -1, i1)
+    assert not ((gi != ridx) & (ridx != -2) & (sw["margin"] > 1e-13)).any()
+
+
+def test_vector_form_on_random_and_grazing_geometries(oracle_dm, oracle_libm):
+    rng = np.random.default_rng(3)
+    radii = np.concatenate([rng.uniform(0.003, 0.15, 400), rng.uniform(0.07, 0.12, 200)])
+    offsets = np.concatenate([rng.uniform(-0.03, 0.03, 400), rng.uniform(-0.05, 0.05, 200)])
+    (t1, k1, i1), (t0, k0, i0), (tl, kl, il) = _tables(oracle_dm, oracle_libm, radii, offsets)
+    assert np.array_equal(k1, k0) and np.array_equal(k1, kl)
+    assert np.array_equal(i1, i0) and np.array_equal(i1, il)
+    hit = k1 >= 0
+    assert hit.sum() > 500 and np.abs(t1 - tl)[hit].max() < 1e-16
+
+
+def test_vector_form_per_ray_nan_pattern(oracle_dm):
+    x_a, z_a = rs.transducer()
+    alpha, zf = rs.launch_angles(), rs.focus_line()
+    p = oracle_dm.params()
+    for r, off in ((0.037, 0.0038), (0.1, -0.01), (0.09, 0.03), (0.005, 0.02)):
+        a = oracle_dm.shoot_rays(p, r, off, x_a[32], z_a[32], zf, alpha)
+        try:
+            oracle_dm.set_math(True)
+            b = oracle_dm.shoot_rays(p, r, off, x_a[32], z_a[32], zf, alpha)
+        finally:
+            oracle_dm.set_math(False)
+        for key in ("a_l", "lens_2_x", "target_x"):
+            assert np.array_equal(np.isnan(a[key]), np.isnan(b[key])), key
+        ok = ~np.isnan(a["target_x"]) & (np.abs(a["a_l"]) < 1e6)      # near-vertical return lines are ill-conditioned in both forms
+        assert np.abs(a["target_x"] - b["target_x"])[ok].max() < 1e-12

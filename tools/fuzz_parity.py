@@ -12,6 +12,7 @@ x_a, z_a = rs.transducer(num_elements=128)
 alpha, zf = rs.launch_angles(), rs.focus_line()
 eng = TofEngine(0).setup(alpha, zf, x_a[64], z_a[64], x_a)
 o = Oracle(device_math=True); p = o.params()
+o.set_math(eng.math_mode == "vector")   # the twin follows the engine's TOFRT_OPT_MATH mode (default: vector)
 rng = np.random.default_rng(2024)
 
 # (1) vs the twin, including idx of every ray
@@ -66,6 +67,7 @@ for i in range(n4):
     rtol, atol = 10.0 ** r4.uniform(-7, -4), 10.0 ** r4.uniform(-7, -4)
     eng.setup(al, zf4, xa[sh], d, xa, rtol=rtol, atol=atol, **kw)
     eng.set_search("guided" if i % 3 else "scan")
+    eng.set_math("vector" if i % 2 else "angle"); o.set_math(bool(i % 2))
     radii = r4.uniform(0.05, 1.1, per) * kw["h0"]; offsets = r4.uniform(-0.3, 0.3, per) * kw["h0"]
     t = eng.tof_table(radii, offsets, records=("idx",))
     p4 = o.params(**kw)
@@ -75,6 +77,22 @@ for i in range(n4):
 out["random_setups_vs_twin_oracle"] = {"setups": n4, "geometries_per_setup": per, "rays": rays, "mismatches": bad,
                                        "varied": "c1, c2, l0, h0, K in [64, 2000), 16-256 elements, pitch, aperture, shooter, rtol/atol, search mode",
                                        "seconds": round(time.time() - t0, 1)}
+eng.set_math("vector"); o.set_math(True)
+# (3b) the two math modes against each other on device: hit decisions identical, times within 1e-15 s
+n6 = int(os.environ.get("FUZZ_MATH_GEOMS", "4000000"))
+eng.setup(alpha, zf, x_a[64], z_a[64], x_a); eng.set_search("guided")
+kdiff = 0; dtmax = 0.0; t0 = time.time()
+for lo in range(0, n6, 1000000):
+    n = min(1000000, n6 - lo)
+    r = torch.from_numpy(rng.uniform(0.002, 0.15, n)).cuda(); of = torch.from_numpy(rng.uniform(-0.04, 0.04, n)).cuda()
+    eng.set_math("angle"); a = eng.tof_table_cuda(r, of); torch.cuda.synchronize()
+    eng.set_math("vector"); b = eng.tof_table_cuda(r, of); torch.cuda.synchronize()
+    kdiff += int((a.k_hit != b.k_hit).sum())
+    both = (a.k_hit >= 0) & (b.k_hit >= 0)
+    dtmax = max(dtmax, float((a.tof - b.tof)[both].abs().max()))
+    del a, b
+out["vector_vs_angle_math"] = {"geometries": n6, "table_entries": n6 * len(x_a), "k_hit_mismatches": kdiff,
+                               "max_abs_dt_s": dtmax, "seconds": round(time.time() - t0, 1)}
 # (4) 3-D two-point solve (extension) vs its CPU twin: bit-identical wherever the start sample agrees
 x65, z65 = rs.transducer()
 eng.setup(rs.launch_angles(), rs.focus_line(), x65[32], z65[32], x65)

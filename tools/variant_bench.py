@@ -28,8 +28,9 @@ else:
     radii, offsets = rs.synthetic_grid(256, 1024)
     r = torch.from_numpy(radii).cuda(); o = torch.from_numpy(offsets).cuda()
     out = {"variant": sys.argv[2], "info": eng.kernel_info()}
-    for mode in ("guided", "scan"):
-        eng.set_search(mode)
+    for mode in ("guided", "scan", "guided+vector", "scan+vector"):
+        eng.set_search(mode.split("+")[0])
+        eng.set_math("vector" if "+vector" in mode else "angle")
         for _ in range(4): eng.tof_table_cuda(r, o)
         torch.cuda.synchronize()
         ts = []
