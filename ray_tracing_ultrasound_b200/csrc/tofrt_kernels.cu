@@ -695,8 +695,8 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
 
 // =====================================================================================
 // FP32 mode (north_star: "FP32 mode reported separately with its measured max error").
-// Same pipeline, per-ray arithmetic in float with CUDA's float elementary functions; the
-// geometry-independent tables are the FP64 ones rounded to float.  No bit-parity is claimed for
+// Same pipeline, per-ray arithmetic in float (interface laws in vector form, MUFU square roots and
+// reciprocals); the geometry-independent tables are the FP64 ones rounded to float.  No bit-parity is claimed for
 // this mode: tests/bench report max |dt| and the hit-decision differences against FP64.
 // =====================================================================================
 struct DevSetupF {
@@ -705,7 +705,7 @@ struct DevSetupF {
     int K, E, E_sorted, has_nonfinite_rx, shape, log2n, n_shooters, surface;
     float h0;
     const float2 *lens, *seg;
-    const float *a_pq, *b_pq, *phi_pq, *z_f, *leg1, *x_rx, *xs;
+    const float *a_pq, *b_pq, *phi_pq, *cpq, *spq, *z_f, *leg1, *x_rx, *xs;
     const int *perm;
 };
 
@@ -724,10 +724,8 @@ __global__ void tofrt_to_float_kernel(int n, const double *src, float *dst)
     if (i < n) dst[i] = (float)src[i];
 }
 
-#define HALF_PI_F 1.57079632679489661923f
-
-// float elementary functions of the FP32 mode: straight-line, ~1 ulp polynomials (Cephes
-// single-precision coefficients), MUFU-based division / square root.  No parity claim here.
+// float helpers of the FP32 mode (MUFU-based square roots; divisions are __fdividef).  The interface
+// laws are evaluated in vector form (see tofrt_raymath.h), so no float elementary functions are needed.
 __device__ __forceinline__ float fsqrt_fast(float x)
 {
     float r;
@@ -741,54 +739,6 @@ __device__ __forceinline__ float fsqrt_fast_ftz(float x)
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ int sincos_reduced_f(float x, float *s, float *c)
-{
-    const float t = fmaf(x, 0.63661975f, 12582912.0f);  // 1.5 * 2^23: round to nearest integer
-    const float n = t - 12582912.0f;
-    const float r = fmaf(-n, -4.371139e-08f, fmaf(-n, 1.5707964f, x));
-    const float z = r * r;
-    *s = fmaf(r * z, fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), r);
-    *c = fmaf(z * z, fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f),
-              fmaf(-0.5f, z, 1.0f));
-    return __float_as_int(t) & 3;
-}
-__device__ __forceinline__ void sincos_f(float x, float *sn, float *cs)
-{
-    float s, c;
-    const int q = sincos_reduced_f(x, &s, &c);
-    float vs = (q & 1) ? c : s, vc = (q & 1) ? s : c;
-    vs = (q & 2) ? -vs : vs;
-    vc = ((q + 1) & 2) ? -vc : vc;
-    const bool ok = fabsf(x) < 1.0e6f;
-    *sn = ok ? vs : NAN;
-    *cs = ok ? vc : NAN;
-}
-__device__ __forceinline__ float tan_f(float x)
-{
-    float s, c;
-    const int q = sincos_reduced_f(x, &s, &c);
-    const float v = (q & 1) ? __fdividef(-c, s) : __fdividef(s, c);
-    return fabsf(x) < 1.0e6f ? v : NAN;
-}
-__device__ __forceinline__ float atan2_f(float y, float x)
-{
-    const float ax = fabsf(x), ay = fabsf(y);
-    const bool swap = ay > ax;
-    const float a = swap ? ax : ay, b = swap ? ay : ax;
-    const bool small = a < 0.41421356f * b;  // tan(pi/8)
-    const float u = __fdividef(small ? a : a - b, small ? b : a + b);
-    const float z = u * u;
-    float r = fmaf(u * z, fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z,
-                               -3.33329491539e-1f), u);
-    r = small ? r : r + 0.78539816339744830962f;
-    r = (b == 0.0f) ? 0.0f : r;
-    r = (a == INFINITY && b == INFINITY) ? 0.78539816339744830962f : r;
-    r = swap ? 1.57079632679489661923f - r : r;
-    r = signbit(x) ? 3.14159265358979323846f - r : r;
-    return copysignf(r, y);
-}
-__device__ __forceinline__ float asin_f(float x) { return atan2_f(x, fsqrt_fast((1.0f - x) * (1.0f + x))); }
-
 __device__ __forceinline__ float line_diff_f(float2 s, float m, float b) { return s.y - (m * s.x + b); }
 __device__ __forceinline__ int sign_class_f(float v) { return v > 0 ? 2 : (v < 0 ? 0 : (v == 0 ? 1 : 3)); }
 __device__ __forceinline__ bool np_isclose_f(float a, float b, float rtol, float atol)
@@ -846,7 +796,8 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
             const int k = (c << 5) + lane;
             const bool valid = k < K;
             const int kk = valid ? k : K - 1;
-            const float a_pq = __ldg(S.a_pq + sk + kk), b_pq = __ldg(S.b_pq + sk + kk), phi_pq = __ldg(S.phi_pq + sk + kk);
+            const float a_pq = __ldg(S.a_pq + sk + kk), b_pq = __ldg(S.b_pq + sk + kk);
+            const float cpq = __ldg(S.cpq + sk + kk), spq = __ldg(S.spq + sk + kk);
             const float z_f = __ldg(S.z_f + kk);
             float x_q, z_q;
             {
@@ -861,13 +812,14 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
                 x_q = up ? x_q1 : x_q2;
                 z_q = up ? z_q1 : z_q2;
             }
-            float phi_l, m, b;
+            float cl, sl, m, b;  // reflected direction r^2 (cos, sin): the vector form of tofrt_raymath.h, in float
             {
-                float slope = __fdividef(-x_q, fsqrt_fast(rsq - x_q * x_q));
-                float phi_slope = atan2_f(slope, 1.0f);
-                float theta_1 = phi_pq - (phi_slope + HALF_PI_F);
-                phi_l = phi_slope - HALF_PI_F + (-theta_1);
-                m = tan_f(phi_l);
+                const float xx = x_q * x_q, ss = rsq - xx;
+                const float s = fsqrt_fast(ss);
+                const float c2 = ss - xx, s2 = (-2.0f * x_q) * s;
+                cl = fmaf(c2, cpq, s2 * spq);
+                sl = fmaf(s2, cpq, -(c2 * spq));
+                m = __fdividef(sl, cl);
                 b = z_q - m * x_q;
             }
             const bool fin = valid && fabsf(m) < 1e18f && fabsf(b) < 1e18f;
@@ -956,15 +908,12 @@ __global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF 
                     dh = __fdividef(S.h0 * sn, cs * cs);
                 }
                 float dz = dh * cs - hh * sn, dx = dh * sn + hh * cs;
-                float phi_slope = atan2_f(dz, dx);
-                float theta_1 = phi_l - (phi_slope + HALF_PI_F);
-                float sn1, cs1;
-                sincos_f(theta_1, &sn1, &cs1);
-                float s_arg = S.c1_over_c2 * sn1;
+                float ihyp;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ihyp) : "f"(fmaf(dx, dx, dz * dz)));
+                float s_arg = S.c1_over_c2 * (-fmaf(cl, dx, sl * dz) * ihyp * __fdividef(1.0f, rsq));
                 if (__any_sync(FULL, valid && fabsf(s_arg) <= 1.0f)) {
-                    float theta_2 = asin_f(s_arg);
-                    float phi_last = phi_slope - HALF_PI_F + theta_2;
-                    float a_i = tan_f(phi_last);
+                    float ct = fsqrt_fast((1.0f - s_arg) * (1.0f + s_arg));   // NaN on total internal reflection
+                    float a_i = __fdividef(fmaf(dz, s_arg, -(dx * ct)), fmaf(dz, ct, dx * s_arg));
                     float b_i = iz - a_i * ix;
                     target_x = __fdividef(z_f - b_i, a_i);
                 }
@@ -1617,7 +1566,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     // ---- FP32 mode: the same tables rounded to float ----
     {
         const int Es = std::max(1, S.E_sorted);
-        const size_t nf = (size_t)4 * K + (size_t)4 * K * NS + K + E + Es;  // lens(2K) seg(2K) [a,b,phi,leg1](S*K) zf x_rx xs
+        const size_t nf = (size_t)4 * K + (size_t)6 * K * NS + K + E + Es;  // lens(2K) seg(2K) [a,b,phi,cos,sin,leg1](S*K) zf x_rx xs
         CUDA_TRY(cudaMalloc(&c->d_f32, sizeof(float) * nf));
         float *f = c->d_f32;
         auto conv = [&](const double *src, int n) {
@@ -1630,6 +1579,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
         F.lens = (const float2 *)conv((const double *)c->d_lens, 2 * K);
         F.seg = (const float2 *)conv((const double *)c->d_seg, 2 * K - 2); f += 2;
         F.a_pq = conv(c->d_a, K * NS); F.b_pq = conv(c->d_b, K * NS); F.phi_pq = conv(c->d_phi, K * NS);
+        F.cpq = conv(c->d_cs, K * NS); F.spq = conv(c->d_cs + (size_t)K * NS, K * NS);
         F.z_f = conv(c->d_zf, K); F.leg1 = conv(c->d_leg1, K * NS);
         F.x_rx = conv(c->d_xrx, E); F.xs = conv(c->d_xs, S.E_sorted);
         CUDA_TRY(cudaGetLastError());
