@@ -202,6 +202,11 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    # stdout carries exactly ONE JSON line: anything a library prints meanwhile (NCCL's version banner at the first
+    # communicator, ...) goes to stderr -- file descriptor 1 is pointed at stderr until the line is written
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -211,8 +216,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     x_a, z_a, alpha, zf, radii, offsets = workload(rank, world, args.grid)
@@ -478,7 +481,10 @@ def main():
                                            "(BASELINE.md section 2) and cannot travel to the GPU box",
                                    "sample": f"{n} of {G} geometries, evenly strided, {dt:.1f} s, oracle C port "
                                              f"(glibc libm), E={E}, K=N={K}"}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
