@@ -36,8 +36,8 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of tofrt_table_kernel from the committed
 # `ncu --set full` captures (profiles/), scaled to the full 1024x1024 grid; None until captured.
-# profiles/ncu_r1_table_kernel.json: 149.4 MB (guided) / 150.7 MB (scan) per 131 072-geometry launch
-NCU_TRAFFIC_BYTES = {"guided": 149.4e6 * 8, "scan": 150.7e6 * 8}
+# profiles/ncu_r1_table_kernel.json: 153.7 MB (guided) / 150.7 MB (scan) per 131 072-geometry launch
+NCU_TRAFFIC_BYTES = {"guided": 153.7e6 * 8, "scan": 150.7e6 * 8}
 
 METRIC = "ray-solves/sec (element x pixel)"
 UNIT = "ray-solves/s"
@@ -438,7 +438,7 @@ def main():
             "roofline_guided": {"kernel_ms": mode_ms["guided"], "achieved": ops / (mode_ms["guided"] * 1e-3) / 1e12,
                                 "frac": ops / (mode_ms["guided"] * 1e-3) / peak_issue},
             "modes_identical": other_same,
-            "fp64_pipe_active_pct_ncu": {"guided": 48.4, "scan": 65.1, "issue_slots_busy_pct": {"guided": 76.8, "scan": 67.7},
+            "fp64_pipe_active_pct_ncu": {"guided": 50.3, "scan": 65.1, "issue_slots_busy_pct": {"guided": 78.3, "scan": 67.7},
                                          "source": "profiles/ncu_r1_table_kernel.json (sm__inst_executed_pipe_fp64, "
                                                    "one --set full capture per mode)"},
             "peak_source": "tofrt_measure_fp64_peak on this GPU (un-fused DMUL+DADD thread-instructions/s); "
