@@ -65,4 +65,6 @@ def test_vector_form_per_ray_nan_pattern(oracle_dm):
         for key in ("a_l", "lens_2_x", "target_x"):
             assert np.array_equal(np.isnan(a[key]), np.isnan(b[key])), key
         ok = ~np.isnan(a["target_x"]) & (np.abs(a["a_l"]) < 1e6)      # near-vertical return lines are ill-conditioned in both forms
-        assert np.abs(a["target_x"] - b["target_x"])[ok].max() < 1e-12
+        if ok.any():   # landing points agree to ~1e-13 of their size (1 mm floor): nothing near the 1e-6 m hit tolerance
+            err = np.abs(a["target_x"] - b["target_x"])[ok] / np.maximum(np.abs(a["target_x"][ok]), 1e-3)
+            assert err.max() < 2e-12
