@@ -6,8 +6,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TOFRT_LIB") or os.path.join(HERE, "libtofrt.so")  # TOFRT_LIB: tuning variants
 SOURCES = [os.path.join(HERE, "csrc", "tofrt_kernels.cu")]
-HEADERS = [os.path.join(HERE, "csrc", "tofrt_math.h"),
-           os.path.join(os.path.dirname(HERE), "include", "tofrt.h")]
+HEADERS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc")))
+           if f.endswith((".h", ".cuh"))] + [os.path.join(os.path.dirname(HERE), "include", "tofrt.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -12,7 +12,7 @@
  *     n(a, b) = (sin a cos b, sin b, cos a cos b)
  *
  * so b = 0 is the reference's x-z plane with a = alpha, where the surface point has the bits of the
- * 2-D lens_point_t of tofrt_kernels.cu.  For an element A on the array plane and a focal point F
+ * 2-D lens_point_t of tofrt_common.cuh.  For an element A on the array plane and a focal point F
  * in the water,
  *
  *     t(a, b) = |A - P(a, b)| / c1 + |P(a, b) - F| / c2

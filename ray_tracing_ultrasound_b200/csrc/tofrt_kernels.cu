@@ -26,6 +26,12 @@
 //   tofrt_fermat_kernel         two-point minimum-time entry point (extension).
 //   tofrt_fp64_peak_kernel      FP64 issue-rate micro-benchmark (the roofline denominator).
 //
+// One translation unit; the device code lives in the .cuh files included below (inside this file's
+// anonymous namespace): tofrt_common.cuh (setup struct, helpers, TMA wrappers), tofrt_setup_kernels.cuh,
+// tofrt_table_kernel.cuh (the hot kernel), tofrt_table_f32.cuh, tofrt_fermat_kernels.cuh,
+// tofrt_misc_kernels.cuh; per-pair/per-ray arithmetic shared with the oracle's twin in tofrt_math.h,
+// tofrt_raymath.h, tofrt_fermat3d.h.  This file holds the context, the host logic and the C ABI.
+//
 // Compile with -fmad=false: the only fused operations are the explicit fma()
 // calls inside tofrt_math.h (shared bit-for-bit with the oracle's twin build).
 #include <cuda_runtime.h>
@@ -49,1248 +55,12 @@
 
 namespace {
 
-#ifndef TOFRT_THREADS
-#define TOFRT_THREADS 896
-#endif
-#ifndef TOFRT_MIN_BLOCKS
-#define TOFRT_MIN_BLOCKS 1
-#endif
-constexpr int kThreadsScan = TOFRT_THREADS;
-constexpr int kThreads = kThreadsScan;  // warps per CTA = kThreads / 32 (literal scan, FP32 mode)
-constexpr int kWarps = kThreads / 32;
-// The guided-search instantiation fits 64 registers, so it runs 1024 threads (32 warps, 8 per
-// scheduler): measured 1.2 % faster than 896; the literal scan is 2 % faster at 896 x 72 registers.
-#ifndef TOFRT_THREADS_GUIDED
-#define TOFRT_THREADS_GUIDED 1024
-#endif
-constexpr int kThreadsGuided = TOFRT_THREADS_GUIDED;
-#ifndef TOFRT_SCAN_CHUNK
-#define TOFRT_SCAN_CHUNK 32
-#endif
-constexpr int kChunk = TOFRT_SCAN_CHUNK;  // lens samples per early-exit check of the literal scan (<= 32)
-constexpr int kNoHit = 0x7fffffff;
-#ifndef TOFRT_CHUNK_MB
-#define TOFRT_CHUNK_MB 64  // output bytes per pipelined chunk of tofrt_table_host
-#endif
-
-// Everything the kernels need that does not depend on the geometry.
-struct DevSetup {
-    // derived constants, computed on the host in the reference's operation order
-    double c1, c2, d;
-    double A, fourAC, twoA, twod, K2, phi1;  // lens surface (main_rt.py:181-212)
-    double c2_over_c1, c1_over_c2;           // v2 / v1 of the two refractions
-    int n_shooters;                          // S: shots per geometry (full-matrix capture when S = E)
-    const double *x_sh, *z_sh;               // [S] shooter positions
-    double rtol, atol, tol_max;              // np.isclose tolerances, and an upper bound of atol+rtol|x_e|
-    double rx_min, rx_max;                   // finite receiver range
-    int K, Npad, E, E_sorted, has_nonfinite_rx, tables_ok;
-    int hits_in_global;  // 1: E too large for the per-warp shared-memory first-hit state -> keep it in the output rows
-    int shape;      // +1: sampled lens strictly concave in x, -1: strictly convex, 0: neither (no guided search)
-    int guided;     // search mode: 1 = guided (bracketed) search, 0 = the reference's literal O(N) scan
-    int vector_math;  // 1: return-path interface laws in vector form (tofrt_raymath.h), 0: the reference's angles
-    int log2n;      // ceil(log2(K)) bisection steps
-    double X, Z;    // max |x_p|, max |z_p|  (rounding-error bound of a diff)
-    int surface;    // 0: the reference's constant-TOF lens h(alpha); 1: flat interface z = h0 (extension)
-    double h0;
-    // tables in global memory
-    const double2 *lens;   // [Npad] (x_p, z_p), padded with copies of the last sample
-    const double2 *seg;    // [K-1] chord (m_seg, b_seg) of main_rt.py:127-128
-    const double *a_pq, *b_pq, *phi_pq, *z_f, *leg1;  // [K]
-    const double *cpq, *spq;  // [K] cos / sin of phi_pq (vector form of the interface laws)
-    const double *x_rx;    // [E] as given
-    const double *xs;      // [E_sorted] finite receivers, ascending
-    const int *perm;       // [E_sorted] original index of xs[i]
-    // candidate lookup: bucket[c] = first i with xs[i] >= bx0 + (c-1)/binv (one cell of slack), nb cells
-    const int *bucket;
-    int nb;
-    double bx0, binv;
-};
-
-struct TableArgs {
-    const double *radius, *offset;
-    long long G;
-    double *tof;
-    int *k_hit;
-    tofrt_ray_records rec;
-    int any_rec;           // any per-ray record requested (besides legs)
-    int s_begin, s_count;  // shooters [s_begin, s_begin + s_count) of the setup; outputs are [s_count][G][...]
-    const double *inject_m, *inject_b;  // test hook (tofrt_debug_search_host): replace the reflected line of ray [w][k]
-    unsigned long long *counter;
-    unsigned long long *stats;  // [4]: rays traced, rays that needed the O(N) scan, warp-chunks that ran it, on-sample passes
-};
-
-// ---- small device helpers ---------------------------------------------------
-
-__device__ __forceinline__ unsigned hi32(double v) { return (unsigned)__double2hiint(v); }
-
-// np.sign class: 0 negative, 1 zero, 2 positive, 3 NaN
-__device__ __forceinline__ int sign_class(double v) { return v > 0 ? 2 : (v < 0 ? 0 : (v == 0 ? 1 : 3)); }
-// np.diff(np.sign(d)) != 0 (NaN - x is NaN and NaN != 0 is True)
-__device__ __forceinline__ bool class_change(int c0, int c1) { return c0 == 3 || c1 == 3 || c0 != c1; }
-
-// np.isclose(a, b, rtol, atol)
-__device__ __forceinline__ bool np_isclose(double a, double b, double rtol, double atol)
-{
-    return ((fabs(a - b) <= atol + rtol * fabs(b)) && isfinite(b)) || (a == b);
-}
-// Python min/max on two floats
-__device__ __forceinline__ double py_min(double a, double b) { return (b < a) ? b : a; }
-__device__ __forceinline__ double py_max(double a, double b) { return (b > a) ? b : a; }
-
-__device__ __forceinline__ double dist2d(double x1, double z1, double x2, double z2)
-{
-    return sqrt((x1 - x2) * (x1 - x2) + (z1 - z2) * (z1 - z2));
-}
-
-// vertical difference of main_rt.py:78-79, two roundings
-__device__ __forceinline__ double line_diff(double2 s, double m, double b) { return s.y - (m * s.x + b); }
-
-// h(alpha), dz/dalpha, dx/dalpha (main_rt.py:180-234); B of :184 and :203 are the same bits
-template <bool FLAT>
-__device__ __forceinline__ void lens_point_t(const DevSetup &S, double sn, double cs, double *h, double *dz,
-                                             double *dx)
-{
-    double hh, dh;
-    if (!FLAT) {
-        double B = S.twod * cs - S.K2;
-        double sd = sqrt(B * B - S.fourAC);
-        hh = (-B - sd) / S.twoA;
-        double dB = -S.twod * sn;
-        double dB2 = 2 * B * dB;
-        double dS = (1 / (2 * sd)) * dB2;
-        dh = S.phi1 * (dB + dS);
-    } else {  // flat interface z = h0 in the same polar form: h = h0 / cos(alpha) (extension, no reference analogue)
-        hh = S.h0 / cs;
-        dh = S.h0 * sn / (cs * cs);
-    }
-    *h = hh;
-    *dz = dh * cs - hh * sn;
-    *dx = dh * sn + hh * cs;
-}
-// run-time surface switch, for the kernels where it does not matter (setup, two-point solve)
-__device__ __forceinline__ void lens_point(const DevSetup &S, double sn, double cs, double *h, double *dz, double *dx)
-{
-    if (S.surface == 0) lens_point_t<false>(S, sn, cs, h, dz, dx);
-    else lens_point_t<true>(S, sn, cs, h, dz, dx);
-}
-
-// refraction of main_rt.py:267-280 with the tuple form of dzdx
-__device__ __forceinline__ double refract(double phi_in, double dz, double dx, double v2_over_v1)
-{
-    double phi_slope = tofrt_atan2(dz, dx);
-    double theta_1 = phi_in - (phi_slope + HALF_PI);
-    double theta_2 = tofrt_asin(v2_over_v1 * tofrt_sin(theta_1));
-    return phi_slope - HALF_PI + theta_2;
-}
-
-// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (cp.async.bulk, sm_90+) ----
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the init visible to the async proxy
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
-{
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
-
-// ---- prepare kernel: main_rt.py:338-349 for every launch angle ----------------
-__global__ void tofrt_prepare_kernel(DevSetup S, const double *alpha, double2 *lens, double *a_pq,
-                                     double *b_pq, double *phi_pq, double *leg1, double *cpq, double *spq, int *bad)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= S.Npad) return;
-    int kk = k < S.K ? k : S.K - 1;  // padding repeats the last sample
-    double al = alpha[kk];
-    double sn, cs, h, dz, dx;
-    tofrt_sincos(al, &sn, &cs);
-    lens_point(S, sn, cs, &h, &dz, &dx);
-    double x_p = h * sn, z_p = h * cs;
-    lens[k] = make_double2(x_p, z_p);
-    if (k >= S.K) return;
-    if (!(fabs(x_p) < 1e150 && fabs(z_p) < 1e150)) atomicOr(bad, 1);
-    for (int s = 0; s < S.n_shooters; ++s) {  // main_rt.py:341-349 for every shooter
-        const double x_sh = S.x_sh[s], z_sh = S.z_sh[s];
-        double phi_ap = tofrt_atan2(z_sh - z_p, x_sh - x_p);
-        double phi = refract(phi_ap, dz, dx, S.c2_over_c1);
-        double a = tofrt_tan(phi);
-        size_t o = (size_t)s * S.K + k;
-        a_pq[o] = a;
-        b_pq[o] = z_p - a * x_p;
-        phi_pq[o] = phi;
-        tofrt_sincos(phi, &spq[o], &cpq[o]);
-        leg1[o] = dist2d(x_sh, z_sh, x_p, z_p) / S.c1;
-    }
-}
-
-// chords of the sampled lens, main_rt.py:127-128 (geometry-independent, so computed once)
-__global__ void tofrt_chord_kernel(int K, const double2 *lens, double2 *seg)
-{
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= K - 1) return;
-    double2 p1 = lens[j], p2 = lens[j + 1];
-    double m_seg = (p2.y - p1.y) / (p2.x - p1.x);
-    double b_seg = p1.y - m_seg * p1.x;
-    seg[j] = make_double2(m_seg, b_seg);
-}
-
-// ---- exact (slow) pieces of find_line_curve_intersection ------------------------
-
-// first j in [j0, N-2] with a sign-class change between samples j and j+1, else -1
-__device__ __noinline__ int scan_exact_from(const double2 *lens, int N, double m, double b, int j0)
-{
-    int cprev = sign_class(line_diff(lens[j0], m, b));
-    for (int j = j0; j + 1 < N; ++j) {
-        int cnext = sign_class(line_diff(lens[j + 1], m, b));
-        if (class_change(cprev, cnext)) return j;
-        cprev = cnext;
-    }
-    return -1;
-}
-
-// main_rt.py:106-168: intersect the line with chord (idx, idx+1)
-__device__ __forceinline__ void chord_intersection(const double2 *lens, const double2 *seg, int idx, double m,
-                                                   double b, double *xi, double *zi)
-{
-    double2 p1 = lens[idx], p2 = lens[idx + 1], sg = seg[idx];
-    double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
-    double rx = NAN, ry = NAN;
-    if (np_isclose(x1, x2, 1e-5, 1e-8)) {  // :110-123 vertical chord
-        double y_int = m * x1 + b;
-        if (y_int >= py_min(y1, y2) - 1e-9 && y_int <= py_max(y1, y2) + 1e-9) { rx = x1; ry = y_int; }
-    } else {
-        double m_seg = sg.x, b_seg = sg.y;  // :127-128
-        if (np_isclose(m, m_seg, 1e-5, 1e-8)) {  // :131-144 parallel
-            if (np_isclose(b, b_seg, 1e-5, 1e-8)) { rx = (x1 + x2) / 2.0; ry = m * rx + b; }
-        } else {  // :147-168
-            double x_int = (b_seg - b) / (m - m_seg);
-            double y_int = m * x_int + b;
-            if (x_int >= py_min(x1, x2) - 1e-9 && x_int <= py_max(x1, x2) + 1e-9 &&
-                y_int >= py_min(y1, y2) - 1e-9 && y_int <= py_max(y1, y2) + 1e-9) {
-                rx = x_int; ry = y_int;
-            }
-        }
-    }
-    *xi = rx; *zi = ry;
-}
-
-// ---- the table kernel -----------------------------------------------------------
-// HG: first-hit state in the output rows (global memory) instead of warp-private shared memory
-// GUIDED: compile the guided search (its rare fallback is then a plain per-ray exact scan) or the
-// warp-wide literal scan -- two lean instruction streams instead of one kernel carrying both.
-// VEC: the two return-path interface laws in vector form (tofrt_raymath.h) instead of the reference's angles
-template <bool HG, bool GUIDED, bool FLAT, bool VEC>
-__global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_BLOCKS)
-    tofrt_table_kernel(DevSetup S, TableArgs T)
-{
-    constexpr int kThreads = GUIDED ? kThreadsGuided : kThreadsScan;  // shadows the namespace constants
-    constexpr int kWarps = kThreads / 32;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int K = S.K, N = S.K, Npad = S.Npad, E = S.E;
-    // shared-memory carve-up
-    double2 *s_lens = reinterpret_cast<double2 *>(smem_raw);
-    double2 *s_seg = s_lens + Npad;                  // [K-1] (+1 pad)
-    double *s_xs = reinterpret_cast<double *>(s_seg + K);
-    double *s_tof = s_xs + S.E_sorted;               // [kWarps][E] (absent when HG)
-    int *s_perm = reinterpret_cast<int *>(s_tof + (HG ? (size_t)0 : (size_t)kWarps * E));
-    int *s_khit = s_perm + S.E_sorted;               // [kWarps][E] (absent when HG)
-    int *s_bucket = s_khit + (HG ? (size_t)0 : (size_t)kWarps * E);  // [nb]
-
-    // Stage the sampled surface once per CTA: two TMA bulk copies (lens samples, chords; 16-byte
-    // aligned, multiples of 16 bytes) complete on one mbarrier while the threads load the small
-    // receiver table themselves.
-    __shared__ __align__(8) unsigned long long s_bar;
-    const unsigned lens_bytes = (unsigned)Npad * (unsigned)sizeof(double2), seg_bytes = (unsigned)K * (unsigned)sizeof(double2);
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(&s_bar, lens_bytes + seg_bytes);
-        tma_bulk_g2s(s_lens, S.lens, lens_bytes, &s_bar);
-        tma_bulk_g2s(s_seg, S.seg, seg_bytes, &s_bar);
-    }
-    for (int i = threadIdx.x; i < S.E_sorted; i += kThreads) { s_xs[i] = S.xs[i]; s_perm[i] = S.perm[i]; }
-    for (int i = threadIdx.x; i < S.nb; i += kThreads) s_bucket[i] = S.bucket[i];
-    while (!mbar_try_wait(&s_bar, 0)) {}
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // first-hit state of the geometry this warp owns: warp-private shared memory, or (large E) the
-    // geometry's own output rows in global memory -- read back with volatile loads, because the
-    // atomicMin below happens in L2 and must not be shadowed by a stale L1 line
-    typedef typename std::conditional<HG, volatile double, double>::type tof_t;
-    typedef typename std::conditional<HG, volatile int, int>::type khit_t;
-    tof_t *w_tof = s_tof + (size_t)warp * E;
-    khit_t *w_khit = s_khit + (size_t)warp * E;
-    const int nchunks = (K + 31) >> 5;
-    const unsigned FULL = 0xffffffffu;
-    const double cand_lo = S.rx_min - S.tol_max, cand_hi = S.rx_max + S.tol_max;  // aperture +- largest tolerance
-    unsigned st_rays = 0, st_scan_rays = 0, st_scan_warps = 0, st_onsample = 0;
-
-    // Work distribution: the CTA takes kWarps consecutive (shooter, geometry) items at a time, one per
-    // warp, and its warps start them together (two block barriers per ~40 us of work).  Warps that
-    // begin a geometry in step run the same code at the same time, which is worth 3.7 % over
-    // fetching per warp (the instruction stream of one chunk is ~40 KB); any tighter coupling
-    // (a barrier every chunk, or every few) costs more than it gives -- measured.
-    __shared__ unsigned long long s_base;
-    const unsigned long long total = (unsigned long long)T.G * (unsigned long long)T.s_count;
-    for (;;) {
-        __syncthreads();  // everyone has read the previous s_base
-        if (threadIdx.x == 0) s_base = atomicAdd(T.counter, (unsigned long long)kWarps);
-        __syncthreads();
-        if (s_base >= total) break;
-        const unsigned long long g64 = s_base + warp;
-        if (g64 >= total) continue;  // tail: fewer items than warps
-        const long long w = (long long)g64;               // work item = (shooter, geometry)
-        long long g = w, s_local = 0;
-        if (T.s_count > 1) { s_local = w / T.G; g = w - s_local * T.G; }  // 64-bit division only when several shooters
-        const size_t sk = (size_t)(T.s_begin + s_local) * K;  // offset of the shooter's per-ray tables
-        const double r_outer = T.radius[g], pipe_offset = T.offset[g];
-        const double rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset;
-        if (HG) { w_tof = T.tof + (size_t)w * E; w_khit = T.k_hit + (size_t)w * E; }
-        for (int e = lane; e < E; e += 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0; }
-        __syncwarp();
-
-        int h1 = -1, h2 = -1;  // guided search: this lane's bracket starts in the previous two chunks
-        for (int c = 0; c < nchunks; ++c) {
-            const int k = (c << 5) + lane;
-            const bool valid = k < K;
-            const int kk = valid ? k : K - 1;
-            // per-ray constants of the shot: one coalesced, L1-resident load per 32 rays
-            const double a_pq = __ldg(S.a_pq + sk + kk), b_pq = __ldg(S.b_pq + sk + kk);
-            const double phi_pq = VEC ? 0.0 : __ldg(S.phi_pq + sk + kk);
-            const double cpq = VEC ? __ldg(S.cpq + sk + kk) : 0.0, spq = VEC ? __ldg(S.spq + sk + kk) : 0.0;
-            const double z_f = __ldg(S.z_f + kk);
-
-            // ---- main_rt.py:351-364 pipe intersection, upper root ----
-            double x_q, z_q;
-            {
-                double A2 = a_pq * a_pq + 1;
-                double B2 = 2 * (a_pq * b_pq - pipe_offset);
-                double C2 = offsq + b_pq * b_pq - rsq;
-                double sd = sqrt(B2 * B2 - 4 * A2 * C2);
-                double den = 2 * A2;
-                double x_q1 = (-B2 + sd) / den, x_q2 = (-B2 - sd) / den;
-                double z_q1 = a_pq * x_q1 + b_pq, z_q2 = a_pq * x_q2 + b_pq;
-                bool up = z_q1 > z_q2;
-                x_q = up ? x_q1 : x_q2;
-                z_q = up ? z_q1 : z_q2;
-            }
-            // ---- main_rt.py:367-376 reflection on the pipe ----
-            double phi_l = 0.0, cl = 0.0, sl = 0.0, m, b;  // reflected direction: angle, or r^2 (cos, sin)
-            if (VEC) {
-                tofrt_vec_reflect(x_q, rsq, cpq, spq, &cl, &sl);
-                m = sl / cl;
-                b = z_q - m * x_q;
-            } else {
-                double slope = -x_q / sqrt(rsq - x_q * x_q);  // dzdx_pipe ignores the offset (:237-238)
-                double phi_slope = tofrt_atan(slope);
-                double theta_1 = phi_pq - (phi_slope + HALF_PI);
-                phi_l = phi_slope - HALF_PI + (-theta_1);
-                m = tofrt_tan(phi_l);
-                b = z_q - m * x_q;
-            }
-            if (T.inject_m) {  // test hook: search an arbitrary line instead (uniform branch, off in production)
-                m = T.inject_m[(size_t)w * K + kk];
-                b = T.inject_b[(size_t)w * K + kk];
-            }
-
-            // ---- main_rt.py:78-99 first sign change over the sampled lens ----
-            // fast path precondition: every diff is finite, so only {-,0,+} occur
-            const bool fast = valid && S.tables_ok && fabs(m) < 1e150 && fabs(b) < 1e150;
-            int idx = -1;             // >= 0 segment, -1 none
-            bool need_scan = fast;    // lanes whose index the O(N) scan below still has to find
-            bool skip_on_sample = false;
-            if (GUIDED) {
-                // ---- guided search: same idx as the scan, in O(log N) diffs ------------------
-                // g_j = shape * diff_j is, in exact arithmetic, a concave sequence over the sampled
-                // lens (chord slopes strictly monotone, checked by tofrt_setup), and a computed diff
-                // differs from the exact one by < tol = 2^-48 (|m| X + |b| + Z).  So a diff beyond
-                // +-tol has a certain sign, a concave sequence is >= the smaller of two of its values
-                // in between, and it is monotone on either side of its maximum: that brackets the
-                // first sign change to [lo, lo+1] with every earlier sign known; the exact scan then
-                // starts at lo.  Anything uncertain (|diff| <= tol where it matters) falls back to the
-                // full scan, so the result is identical by construction.
-                const double sh = (double)S.shape;
-                const double tol = (fabs(m) * S.X + fabs(b) + S.Z) * 0x1p-48 + 1e-290;
-                const double g0 = sh * line_diff(s_lens[0], m, b);
-                const double gN = sh * line_diff(s_lens[N - 1], m, b);
-                const bool pos0 = g0 > tol, neg0 = g0 < -tol;
-                bool bracket = false, certain_none = false;
-                double edge = 0.0;  // lower bound of min|diff| when there is certainly no change
-                if (fast && pos0 && gN > tol) { certain_none = true; edge = fmin(g0, gN) - tol; }
-                else if (fast && (pos0 || neg0)) bracket = true;
-                // One bisection serves both cases.  lo advances to mid iff g_mid certainly has the
-                // sign of g_0 and, when g_0 < 0, mid is still before the maximum of g (chord slope
-                // on the rising side): then every sample up to mid certainly has that sign too.
-                const double sgn = pos0 ? sh : -sh;
-                const double ms_eff = pos0 ? -INFINITY : sh * m;
-                // "diff_mid certainly has the sign of diff_0", one fused operation per probe:
-                //   sgn (z - m x - b) > tol   <=   sgn z > fma(sgn m, x, sgn b + tol)
-                // (sgn = +-1: the products are exact; the two roundings are < tol/16, see docs/guided_search.md)
-                const double cm = sgn * m, cbt = sgn * b + tol;
-                const int zflip = sgn < 0.0 ? (int)0x80000000 : 0;
-                const int sflip = S.shape < 0 ? (int)0x80000000 : 0;  // uniform: sh * slope by a sign flip
-                const char *lens_b = reinterpret_cast<const char *>(s_lens);
-                const int slope_off = (int)(reinterpret_cast<const char *>(s_seg) - lens_b);  // uniform
-                // cond(j): sample j certainly has the sign of g_0 and (g_0 < 0) lies on the rising side.  ANY j
-                // with cond(j) is a valid lower end of the bracket, any j without it a valid upper end
-                // (the concavity arguments do not depend on how j was chosen, docs/guided_search.md).
-                auto cond_at = [&](int j) {
-                    const char *pa = lens_b + j * 16;  // lens[j]; the chord slope sits slope_off bytes further
-                    const double2 pm = *reinterpret_cast<const double2 *>(pa);
-                    const double slope = *reinterpret_cast<const double *>(pa + slope_off);
-                    const double zs = __hiloint2double(__double2hiint(pm.y) ^ zflip, __double2loint(pm.y));
-                    const double ss = __hiloint2double(__double2hiint(slope) ^ sflip, __double2loint(slope));
-                    return (zs > fma(cm, pm.x, cbt)) && (ss > ms_eff);
-                };
-                int lo = 0, hi = N - 1, nsteps = S.log2n;
-                // Predicted bracket: along a shot the entry index is a smooth function of the ray index, so
-                // this lane's brackets of the previous two chunks extrapolate to within a few samples
-                // (measured on config 3: +-4 covers 96 % of the chunks, +-8 99.6 %).  Two probes certify [p - W, p + W] as a
-                // bracket for every lane of the warp, and the bisection needs log2(2 W) steps instead of
-                // log2(N); otherwise the full bisection runs as before.
-#ifndef TOFRT_PRED_W  /* measured: W = 4 (3 steps) 7.81 ms, W = 8 (4 steps) 7.91 ms, W = 16 (5 steps) 8.11 ms; none: 8.44 ms */
-#define TOFRT_PRED_W 4
-#define TOFRT_PRED_STEPS 3
-#endif
-                constexpr int kPredW = TOFRT_PRED_W, kPredSteps = TOFRT_PRED_STEPS;  // 2 * kPredW <= 2^kPredSteps
-                if (__all_sync(FULL, !bracket || (h1 >= 0 && h2 >= 0))) {
-                    const int p = 2 * h1 - h2;
-                    const int plo = min(max(p - kPredW, 0), N - 2), phi = min(plo + 2 * kPredW, N - 1);
-                    const bool okp = cond_at(plo) && !cond_at(phi);
-                    if (__all_sync(FULL, !bracket || okp)) { lo = plo; hi = phi; nsteps = kPredSteps; }
-                }
-                for (int it = 0; it < nsteps; ++it) {
-                    const int mid = (lo + hi) >> 1;  // <= N-2 whenever hi - lo > 1
-                    const bool cond = cond_at(mid);
-                    const bool act = bracket && (hi - lo > 1);
-                    lo = (act && cond) ? mid : lo;
-                    hi = (act && !cond) ? mid : hi;
-                }
-                h2 = h1;
-                h1 = bracket ? lo : -1;
-                if (bracket && hi - lo > 1) { bracket = false; }  // cannot happen (log2n steps suffice); scan if it did
-                if (bracket && neg0) {
-                    // hi = lo + 1 failed the test (or is the untested last sample).  If g_hi is still
-                    // certainly negative, hi is at/after the maximum while lo is before it: g_hi IS
-                    // the maximum of g, so no diff is >= 0.
-                    // (lo == 0 was never tested against the slope: if g already falls from the first
-                    // sample on, the maximum is g_0 -- so the bound below uses the larger of the two)
-                    // ("certainly negative" must be the loop's own probe: hi may have failed exactly that)
-                    const double2 ph = s_lens[hi];
-                    const double ghi = sh * line_diff(ph, m, b);
-                    const double glo = sh * line_diff(s_lens[lo], m, b);
-                    const double zh = __hiloint2double(__double2hiint(ph.y) ^ zflip, __double2loint(ph.y));
-                    if (zh > fma(cm, ph.x, cbt)) { bracket = false; certain_none = true; edge = -fmax(ghi, glo) - tol; }
-                }
-                if (bracket) {
-                    // exact classes from lo on (normally one step)
-                    int cprev = sign_class(line_diff(s_lens[lo], m, b));
-                    int j = lo;
-                    for (; j + 1 < N; ++j) {
-                        int cnext = sign_class(line_diff(s_lens[j + 1], m, b));
-                        if (class_change(cprev, cnext)) break;
-                        cprev = cnext;
-                    }
-                    if (j + 1 < N) idx = j;
-                    need_scan = false;  // no change after lo either => none at all (on-sample test decides)
-                } else if (certain_none) {
-                    need_scan = false;
-                    skip_on_sample = edge > 1e-8;  // every |diff| > 1e-8: main_rt.py:86-96 returns None
-                }
-            }
-            int flagged = -1;
-            unsigned gmin = 0xffffffffu;  // min over all chunks of the high words (see below)
-            st_rays += valid; st_scan_rays += need_scan;
-            if (GUIDED) {
-                // a ray the guided search could not decide (|diff| <= tol where it matters): plain exact scan
-                if (__any_sync(FULL, need_scan)) st_scan_warps += (lane == 0);
-                if (need_scan) { idx = scan_exact_from(s_lens, N, m, b, 0); flagged = 0; }
-            } else if (__any_sync(FULL, need_scan)) {
-                st_scan_warps += (lane == 0);
-                unsigned hp = hi32(line_diff(s_lens[0], m, b));
-                for (int base = 1; base < Npad; base += kChunk) {
-                    unsigned mn = hp, mx = hp;
-#pragma unroll
-                    for (int u = 0; u < kChunk; u += 2) {
-                        unsigned ha = hi32(line_diff(s_lens[base + u], m, b));
-                        unsigned hb = hi32(line_diff(s_lens[base + u + 1], m, b));
-                        mn = __vimin3_u32(mn, ha, hb);
-                        mx = __vimax3_u32(mx, ha, hb);
-                        hp = hb;
-                    }
-                    gmin = min(gmin, mn);
-                    // sign differs inside the chunk, or a +-0 (high word 0 / 0x80000000) occurred
-                    bool flag = ((int)(mn ^ mx) < 0) || ((mn << 1) == 0u);
-                    if (flag && flagged < 0) flagged = base;
-                    if (__all_sync(FULL, flagged >= 0 || !need_scan)) break;
-                }
-            }
-            if (!GUIDED && need_scan && flagged >= 0) {
-                // resolve the exact index inside the flagged chunk without a data-dependent loop:
-                // classes (-1, 0, +1) of samples flagged-1 .. flagged+kChunk-1 (all finite here),
-                // bit u of `chg` = class changes between samples j0+u and j0+u+1
-                const int j0 = flagged - 1;
-                double d = line_diff(s_lens[j0], m, b);
-                int cprev = (((unsigned)__double2hiint(d) << 1) | (unsigned)__double2loint(d)) ? (__double2hiint(d) >> 31) | 1 : 0;
-                unsigned chg = 0;
-#pragma unroll
-                for (int u = 0; u < kChunk; ++u) {
-                    d = line_diff(s_lens[j0 + u + 1], m, b);
-                    int cnext = (((unsigned)__double2hiint(d) << 1) | (unsigned)__double2loint(d)) ? (__double2hiint(d) >> 31) | 1 : 0;
-                    chg |= (cnext != cprev ? 1u : 0u) << u;
-                    cprev = cnext;
-                }
-                if (chg) idx = j0 + __ffs(chg) - 1;  // padding repeats the last sample: never a change there
-            }
-            if (valid && idx < 0) {
-                if (!fast) idx = scan_exact_from(s_lens, N, m, b, 0);
-                // conservative flag without a real change (a denormal diff): keep going exactly
-                else if (!GUIDED && need_scan && flagged >= 0 && flagged + kChunk - 1 < N - 1)
-                    idx = scan_exact_from(s_lens, N, m, b, flagged + kChunk - 1);
-            }
-            // ---- main_rt.py:84-96 no crossing: is a sample on the line (|diff| <= 1e-8)? ----
-            // All diffs of such a ray have one sign, so the unsigned minimum of their high words is
-            // the high word of min|diff|: only rays that come within 1e-8 of a sample (hi <= hi(1e-8))
-            // need the test.  It is warp-cooperative: 32 lanes take 32 consecutive samples of one ray.
-            int on_sample = -1;
-            {
-                bool maybe = valid && idx < 0 && !skip_on_sample &&
-                             (!fast || !need_scan || flagged >= 0 ||
-                              (gmin & 0x7fffffffu) <= 0x3e45798eu /* hi32(1e-8) */);
-                unsigned need = __ballot_sync(FULL, maybe);
-                st_onsample += (lane == 0) ? __popc(need) : 0;
-                while (need) {
-                    int src = __ffs(need) - 1;
-                    need &= need - 1;
-                    double mm = __shfl_sync(FULL, m, src), bb = __shfl_sync(FULL, b, src);
-                    int first = kNoHit;
-                    for (int j = lane; j < N; j += 32) {
-                        double dd = line_diff(s_lens[j], mm, bb);
-                        if (fabs(dd) <= 1e-8) { first = j; break; }
-                    }
-                    first = __reduce_min_sync(FULL, first);
-                    if (lane == src && first != kNoHit) on_sample = first;
-                }
-            }
-            double ix = NAN, iz = NAN;
-            if (idx >= 0) chord_intersection(s_lens, s_seg, idx, m, b, &ix, &iz);
-            else if (on_sample >= 0) { double2 s = s_lens[on_sample]; ix = s.x; iz = s.y; }
-
-            // ---- main_rt.py:396-405 refraction back into the lens, landing point ----
-            // NaN in -> NaN out, so whole 32-ray groups that missed the lens, or are totally
-            // reflected (|sin| > 1 in main_rt.py:277), skip the rest of the arithmetic.
-            double target_x = NAN;
-            if (__any_sync(FULL, valid && ix == ix)) {
-                // alpha_i = arctan2(ix, iz) is only ever used through sin/cos (main_rt.py:396-397):
-                // one fused elementary function, no angle
-                double sn, cs, h, dz, dx;
-                tofrt_sincos_atan2(ix, iz, &sn, &cs);
-                lens_point_t<FLAT>(S, sn, cs, &h, &dz, &dx);
-                // refraction(phi_l, (dz, dx), c2, c1), main_rt.py:272-278
-                double phi_slope = 0.0, s_arg;
-                if (VEC) s_arg = S.c1_over_c2 * tofrt_vec_sin_theta1(cl, sl, rsq, dz, dx);
-                else {
-                    phi_slope = tofrt_atan2(dz, dx);
-                    double theta_1 = phi_l - (phi_slope + HALF_PI);
-                    s_arg = S.c1_over_c2 * tofrt_sin(theta_1);
-                }
-                if (__any_sync(FULL, valid && fabs(s_arg) <= 1.0)) {
-                    double a_i;
-                    if (VEC) a_i = tofrt_vec_refract_slope(s_arg, dz, dx);
-                    else {
-                        double theta_2 = tofrt_asin(s_arg);
-                        double phi_last = phi_slope - HALF_PI + theta_2;
-                        a_i = tofrt_tan(phi_last);
-                    }
-                    double b_i = iz - a_i * ix;
-                    target_x = (z_f - b_i) / a_i;
-                }
-            }
-
-            // ---- optional per-ray records ----
-            if (T.any_rec && valid) {  // one uniform test in table-only mode
-                size_t o = (size_t)w * K + k;
-                if (T.rec.pipe_x) T.rec.pipe_x[o] = x_q;
-                if (T.rec.pipe_z) T.rec.pipe_z[o] = z_q;
-                if (T.rec.lens2_x) T.rec.lens2_x[o] = ix;
-                if (T.rec.lens2_z) T.rec.lens2_z[o] = iz;
-                if (T.rec.target_x) T.rec.target_x[o] = target_x;
-                if (T.rec.idx) T.rec.idx[o] = idx >= 0 ? idx : (on_sample >= 0 ? -2 - on_sample : -1);
-            }
-
-            // ---- main_rt.py:487-501 which receivers does this ray land on? ----
-            // candidates: finite receivers within tol_max of target_x (binary search in the
-            // sorted copy); the exact np.isclose decides.  +-inf landing points can only match
-            // an identical infinite receiver.
-            bool cand = valid && target_x >= cand_lo && target_x <= cand_hi;
-            bool special = valid && S.has_nonfinite_rx && isinf(target_x);
-            const bool want_legs = T.rec.legs != nullptr;
-            if (__any_sync(FULL, cand || special || want_legs)) {
-                int lo = 0, hi = 0;
-                bool mine = false;
-                if (cand) {
-                    double tl = target_x - S.tol_max, th = target_x + S.tol_max;
-                    // first sorted receiver >= tl: a bucket lookup (start provably at or before it)
-                    // plus a short forward walk; binary search when no bucket table was built
-                    int l = 0;
-                    if (S.nb > 0) {
-                        const double cpos = (tl - S.bx0) * S.binv;
-                        const int c = cpos > 0.0 ? (cpos < (double)(S.nb - 1) ? (int)cpos : S.nb - 1) : 0;
-                        l = s_bucket[c];
-                        while (l < S.E_sorted && s_xs[l] < tl) ++l;
-                    } else {
-                        int r = S.E_sorted;
-                        while (l < r) { int mid = (l + r) >> 1; if (s_xs[mid] < tl) l = mid + 1; else r = mid; }
-                    }
-                    lo = l;
-                    hi = l;
-                    while (hi < S.E_sorted && s_xs[hi] <= th) ++hi;
-                    for (int i = lo; i < hi; ++i)
-                        if (np_isclose(target_x, s_xs[i], S.rtol, S.atol)) { atomicMin(const_cast<int *>(&w_khit[s_perm[i]]), k); mine = true; }
-                }
-                if (special) {
-                    for (int e = 0; e < E; ++e)
-                        if (target_x == S.x_rx[e]) { atomicMin(const_cast<int *>(&w_khit[e]), k); mine = true; }
-                }
-                __syncwarp();
-                if (mine || (want_legs && valid)) {
-                    // main_rt.py:497-500 / main_compare.py:514-517
-                    double2 p = s_lens[kk];
-                    double t1 = S.leg1[sk + kk];
-                    double t2 = dist2d(p.x, p.y, x_q, z_q) / S.c2;
-                    double t3 = dist2d(x_q, z_q, ix, iz) / S.c2;
-                    double t4 = dist2d(ix, iz, target_x, z_f) / S.c1;
-                    if (want_legs) {
-                        size_t o = (size_t)w * 4 * K + k;
-                        T.rec.legs[o] = t1; T.rec.legs[o + K] = t2;
-                        T.rec.legs[o + 2 * (size_t)K] = t3; T.rec.legs[o + 3 * (size_t)K] = t4;
-                    }
-                    if (mine) {
-                        double tof = t1;
-                        tof += t2;
-                        tof += t3;
-                        tof += t4;
-                        for (int i = lo; i < hi; ++i) {
-                            int e = s_perm[i];
-                            if (w_khit[e] == k) w_tof[e] = tof;
-                        }
-                        if (special)
-                            for (int e = 0; e < E; ++e)
-                                if (w_khit[e] == k) w_tof[e] = tof;
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        // ---- one geometry done: coalesced row of the [G][E] table ----
-        __syncwarp();
-        for (int e = lane; e < E; e += 32) {
-            int kh = w_khit[e];
-            if (!HG) T.tof[(size_t)w * E + e] = w_tof[e];
-            T.k_hit[(size_t)w * E + e] = kh == kNoHit ? -1 : kh;
-        }
-        __syncwarp();
-    }
-    if (T.stats) {
-        st_rays = __reduce_add_sync(FULL, st_rays); st_scan_rays = __reduce_add_sync(FULL, st_scan_rays);
-        if (lane == 0) {
-            atomicAdd(T.stats + 0, (unsigned long long)st_rays); atomicAdd(T.stats + 1, (unsigned long long)st_scan_rays);
-            atomicAdd(T.stats + 2, (unsigned long long)st_scan_warps); atomicAdd(T.stats + 3, (unsigned long long)st_onsample);
-        }
-    }
-}
-
-// =====================================================================================
-// FP32 mode (north_star: "FP32 mode reported separately with its measured max error").
-// Same pipeline, per-ray arithmetic in float (interface laws in vector form, MUFU square roots and
-// reciprocals); the geometry-independent tables are the FP64 ones rounded to float.  No bit-parity is claimed for
-// this mode: tests/bench report max |dt| and the hit-decision differences against FP64.
-// =====================================================================================
-struct DevSetupF {
-    float c1, c2, fourAC, twoA, twod, K2, phi1, c1_over_c2;
-    float rtol, atol, tol_max, rx_min, rx_max, X, Z;
-    int K, E, E_sorted, has_nonfinite_rx, shape, log2n, n_shooters, surface;
-    float h0;
-    const float2 *lens, *seg;
-    const float *a_pq, *b_pq, *phi_pq, *cpq, *spq, *z_f, *leg1, *x_rx, *xs;
-    const int *perm;
-};
-
-struct TableArgsF {
-    const double *radius, *offset;
-    long long G;
-    float *tof;
-    int *k_hit;
-    int s_begin, s_count;
-    unsigned long long *counter;
-};
-
-__global__ void tofrt_to_float_kernel(int n, const double *src, float *dst)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = (float)src[i];
-}
-
-// float helpers of the FP32 mode (MUFU-based square roots; divisions are __fdividef).  The interface
-// laws are evaluated in vector form (see tofrt_raymath.h), so no float elementary functions are needed.
-__device__ __forceinline__ float fsqrt_fast(float x)
-{
-    float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-// flush-to-zero variant: no denormal pre-scaling around the MUFU (screening passes only)
-__device__ __forceinline__ float fsqrt_fast_ftz(float x)
-{
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float line_diff_f(float2 s, float m, float b) { return s.y - (m * s.x + b); }
-__device__ __forceinline__ int sign_class_f(float v) { return v > 0 ? 2 : (v < 0 ? 0 : (v == 0 ? 1 : 3)); }
-__device__ __forceinline__ bool np_isclose_f(float a, float b, float rtol, float atol)
-{
-    return ((fabsf(a - b) <= atol + rtol * fabsf(b)) && isfinite(b)) || (a == b);
-}
-__device__ __forceinline__ float dist2d_f(float x1, float z1, float x2, float z2)
-{
-    return sqrtf((x1 - x2) * (x1 - x2) + (z1 - z2) * (z1 - z2));
-}
-__device__ __noinline__ int scan_exact_from_f(const float2 *lens, int N, float m, float b, int j0)
-{
-    int cprev = sign_class_f(line_diff_f(lens[j0], m, b));
-    for (int j = j0; j + 1 < N; ++j) {
-        int cnext = sign_class_f(line_diff_f(lens[j + 1], m, b));
-        if (class_change(cprev, cnext)) return j;
-        cprev = cnext;
-    }
-    return -1;
-}
-
-__global__ void __launch_bounds__(kThreads, 1) tofrt_table_kernel_f32(DevSetupF S, TableArgsF T)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int K = S.K, N = S.K, E = S.E;
-    float2 *s_lens = reinterpret_cast<float2 *>(smem_raw);
-    float2 *s_seg = s_lens + N;
-    float *s_xs = reinterpret_cast<float *>(s_seg + N);
-    float *s_tof = s_xs + S.E_sorted;                 // [kWarps][E]
-    int *s_perm = reinterpret_cast<int *>(s_tof + (size_t)kWarps * E);
-    int *s_khit = s_perm + S.E_sorted;                // [kWarps][E]
-    for (int i = threadIdx.x; i < N; i += kThreads) s_lens[i] = S.lens[i];
-    for (int i = threadIdx.x; i < N - 1; i += kThreads) s_seg[i] = S.seg[i];
-    for (int i = threadIdx.x; i < S.E_sorted; i += kThreads) { s_xs[i] = S.xs[i]; s_perm[i] = S.perm[i]; }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *w_tof = s_tof + (size_t)warp * E;
-    int *w_khit = s_khit + (size_t)warp * E;
-    const int nchunks = (K + 31) >> 5;
-    const unsigned FULL = 0xffffffffu;
-    for (;;) {  // per-warp work fetch (the CTA-level fetch of the FP64 kernel measured 5 % slower here)
-        unsigned long long g64 = 0;
-        if (lane == 0) g64 = atomicAdd(T.counter, 1ull);
-        g64 = __shfl_sync(FULL, g64, 0);
-        if (g64 >= (unsigned long long)T.G * (unsigned long long)T.s_count) break;
-        const long long w = (long long)g64;
-        const long long g = w % T.G;
-        const size_t sk = (size_t)(T.s_begin + w / T.G) * K;
-        const float r_outer = (float)T.radius[g], pipe_offset = (float)T.offset[g];
-        const float rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset;
-        for (int e = lane; e < E; e += 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0f; }
-        __syncwarp();
-        for (int c = 0; c < nchunks; ++c) {
-            const int k = (c << 5) + lane;
-            const bool valid = k < K;
-            const int kk = valid ? k : K - 1;
-            const float a_pq = __ldg(S.a_pq + sk + kk), b_pq = __ldg(S.b_pq + sk + kk);
-            const float cpq = __ldg(S.cpq + sk + kk), spq = __ldg(S.spq + sk + kk);
-            const float z_f = __ldg(S.z_f + kk);
-            float x_q, z_q;
-            {
-                float A2 = a_pq * a_pq + 1;
-                float B2 = 2 * (a_pq * b_pq - pipe_offset);
-                float C2 = offsq + b_pq * b_pq - rsq;
-                float sd = fsqrt_fast(B2 * B2 - 4 * A2 * C2);
-                float den = 2 * A2;
-                float x_q1 = __fdividef(-B2 + sd, den), x_q2 = __fdividef(-B2 - sd, den);
-                float z_q1 = a_pq * x_q1 + b_pq, z_q2 = a_pq * x_q2 + b_pq;
-                bool up = z_q1 > z_q2;
-                x_q = up ? x_q1 : x_q2;
-                z_q = up ? z_q1 : z_q2;
-            }
-            float cl, sl, m, b;  // reflected direction r^2 (cos, sin): the vector form of tofrt_raymath.h, in float
-            {
-                const float xx = x_q * x_q, ss = rsq - xx;
-                const float s = fsqrt_fast(ss);
-                const float c2 = ss - xx, s2 = (-2.0f * x_q) * s;
-                cl = fmaf(c2, cpq, s2 * spq);
-                sl = fmaf(s2, cpq, -(c2 * spq));
-                m = __fdividef(sl, cl);
-                b = z_q - m * x_q;
-            }
-            const bool fin = valid && fabsf(m) < 1e18f && fabsf(b) < 1e18f;
-            int idx = -1;
-            bool need_scan = fin, check_on_sample = false;
-            if (S.shape != 0) {  // the guided search of the FP64 kernel, in float (tol = 2^-19 (...))
-                const float sh = (float)S.shape;
-                const float tol = (fabsf(m) * S.X + fabsf(b) + S.Z) * 1.9073486328125e-06f /* 2^-19 */ + 1e-30f;
-                const float g0 = sh * line_diff_f(s_lens[0], m, b), gN = sh * line_diff_f(s_lens[N - 1], m, b);
-                const bool pos0 = g0 > tol, neg0 = g0 < -tol;
-                bool bracket = false, none = false;
-                float edge = 0.f;
-                if (fin && pos0 && gN > tol) { none = true; edge = fminf(g0, gN) - tol; }
-                else if (fin && (pos0 || neg0)) bracket = true;
-                const float sgn = pos0 ? sh : -sh;
-                const float ms_eff = pos0 ? -INFINITY : sh * m;
-                int lo = 0, hi = N - 1;
-                for (int it = 0; it < S.log2n; ++it) {
-                    const int mid = (lo + hi) >> 1;
-                    const bool cond = (sgn * line_diff_f(s_lens[mid], m, b) > tol) && (sh * s_seg[mid].x > ms_eff);
-                    const bool act = bracket && (hi - lo > 1);
-                    lo = (act && cond) ? mid : lo;
-                    hi = (act && !cond) ? mid : hi;
-                }
-                if (bracket && hi - lo > 1) bracket = false;
-                if (bracket && neg0) {
-                    const float ghi = sh * line_diff_f(s_lens[hi], m, b), glo = sh * line_diff_f(s_lens[lo], m, b);
-                    if (ghi < -tol) { bracket = false; none = true; edge = -fmaxf(ghi, glo) - tol; }
-                }
-                if (bracket) {
-                    int cprev = sign_class_f(line_diff_f(s_lens[lo], m, b));
-                    int j = lo;
-                    for (; j + 1 < N; ++j) {
-                        int cnext = sign_class_f(line_diff_f(s_lens[j + 1], m, b));
-                        if (class_change(cprev, cnext)) break;
-                        cprev = cnext;
-                    }
-                    if (j + 1 < N) idx = j;
-                    need_scan = false;
-                    check_on_sample = idx < 0;
-                } else if (none) {
-                    need_scan = false;
-                    check_on_sample = !(edge > 1e-8f);
-                }
-            }
-            if (valid && need_scan) { idx = scan_exact_from_f(s_lens, N, m, b, 0); check_on_sample = idx < 0; }
-            else if (valid && !fin) idx = scan_exact_from_f(s_lens, N, m, b, 0);
-            float ix = NAN, iz = NAN;
-            if (idx >= 0) {
-                float2 p1 = s_lens[idx], p2 = s_lens[idx + 1], sg = s_seg[idx];
-                if (np_isclose_f(p1.x, p2.x, 1e-5f, 1e-8f)) {
-                    float y_int = m * p1.x + b;
-                    if (y_int >= fminf(p1.y, p2.y) - 1e-9f && y_int <= fmaxf(p1.y, p2.y) + 1e-9f) { ix = p1.x; iz = y_int; }
-                } else if (np_isclose_f(m, sg.x, 1e-5f, 1e-8f)) {
-                    if (np_isclose_f(b, sg.y, 1e-5f, 1e-8f)) { ix = (p1.x + p2.x) / 2.0f; iz = m * ix + b; }
-                } else {
-                    float x_int = __fdividef(sg.y - b, m - sg.x), y_int = m * x_int + b;
-                    if (x_int >= fminf(p1.x, p2.x) - 1e-9f && x_int <= fmaxf(p1.x, p2.x) + 1e-9f &&
-                        y_int >= fminf(p1.y, p2.y) - 1e-9f && y_int <= fmaxf(p1.y, p2.y) + 1e-9f) { ix = x_int; iz = y_int; }
-                }
-            } else if (valid && check_on_sample) {
-                for (int j = 0; j < N; ++j)
-                    if (fabsf(line_diff_f(s_lens[j], m, b)) <= 1e-8f) { ix = s_lens[j].x; iz = s_lens[j].y; break; }
-            }
-            float target_x = NAN;
-            if (__any_sync(FULL, valid && ix == ix)) {
-                // sin/cos of atan2(ix, iz) without the angle, as in the FP64 kernel
-                float sn, cs;
-                {
-                    const float r2 = fmaf(ix, ix, iz * iz);
-                    float inv;
-                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r2));
-                    sn = ix * inv;
-                    cs = iz * inv;
-                }
-                float hh, dh;
-                if (S.surface == 0) {
-                    float B = S.twod * cs - S.K2;
-                    float sd = fsqrt_fast(B * B - S.fourAC);
-                    hh = __fdividef(-B - sd, S.twoA);
-                    float dB = -S.twod * sn;
-                    float dS = __fdividef(1.0f, 2 * sd) * (2 * B * dB);
-                    dh = S.phi1 * (dB + dS);
-                } else {
-                    hh = __fdividef(S.h0, cs);
-                    dh = __fdividef(S.h0 * sn, cs * cs);
-                }
-                float dz = dh * cs - hh * sn, dx = dh * sn + hh * cs;
-                float ihyp;
-                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ihyp) : "f"(fmaf(dx, dx, dz * dz)));
-                float s_arg = S.c1_over_c2 * (-fmaf(cl, dx, sl * dz) * ihyp * __fdividef(1.0f, rsq));
-                if (__any_sync(FULL, valid && fabsf(s_arg) <= 1.0f)) {
-                    float ct = fsqrt_fast((1.0f - s_arg) * (1.0f + s_arg));   // NaN on total internal reflection
-                    float a_i = __fdividef(fmaf(dz, s_arg, -(dx * ct)), fmaf(dz, ct, dx * s_arg));
-                    float b_i = iz - a_i * ix;
-                    target_x = __fdividef(z_f - b_i, a_i);
-                }
-            }
-            bool cand = valid && target_x >= S.rx_min - S.tol_max && target_x <= S.rx_max + S.tol_max;
-            bool special = valid && S.has_nonfinite_rx && isinf(target_x);
-            if (__any_sync(FULL, cand || special)) {
-                int lo = 0, hi = 0;
-                bool mine = false;
-                if (cand) {
-                    float tl = target_x - S.tol_max, th = target_x + S.tol_max;
-                    int l = 0, r = S.E_sorted;
-                    while (l < r) { int mid = (l + r) >> 1; if (s_xs[mid] < tl) l = mid + 1; else r = mid; }
-                    lo = hi = l;
-                    while (hi < S.E_sorted && s_xs[hi] <= th) ++hi;
-                    for (int i = lo; i < hi; ++i)
-                        if (np_isclose_f(target_x, s_xs[i], S.rtol, S.atol)) { atomicMin(&w_khit[s_perm[i]], k); mine = true; }
-                }
-                if (special)
-                    for (int e = 0; e < E; ++e)
-                        if (target_x == S.x_rx[e]) { atomicMin(&w_khit[e], k); mine = true; }
-                __syncwarp();
-                if (mine) {
-                    float2 p = s_lens[kk];
-                    float tof = S.leg1[sk + kk];
-                    tof += dist2d_f(p.x, p.y, x_q, z_q) / S.c2;
-                    tof += dist2d_f(x_q, z_q, ix, iz) / S.c2;
-                    tof += dist2d_f(ix, iz, target_x, z_f) / S.c1;
-                    for (int i = lo; i < hi; ++i) { int e = s_perm[i]; if (w_khit[e] == k) w_tof[e] = tof; }
-                    if (special) for (int e = 0; e < E; ++e) if (w_khit[e] == k) w_tof[e] = tof;
-                }
-                __syncwarp();
-            }
-        }
-        __syncwarp();
-        for (int e = lane; e < E; e += 32) {
-            int kh = w_khit[e];
-            T.tof[(size_t)w * E + e] = w_tof[e];
-            T.k_hit[(size_t)w * E + e] = kh == kNoHit ? -1 : kh;
-        }
-        __syncwarp();
-    }
-}
-
-// =====================================================================================
-// Two-point Fermat solve (SURVEY.md row f4 -- BASELINE.json north_star's literal wording).
-// For every (array element e, focal point F) pair: the lens entry point P(alpha) that minimises
-//     t(alpha) = |A_e - P(alpha)| / c1 + |P(alpha) - F| / c2
-// over the lens surface of the current setup -- discrete argmin over the N lens samples, then a
-// safeguarded secant (Illinois) iteration on dt/dalpha inside the two neighbouring sample
-// intervals, using the reference's own h(alpha), dh/dalpha (main_rt.py:180-234).  The reference
-// has no such function: parity is unpinned; the checker is a NumPy/SciPy oracle plus analytic
-// known answers (tests/test_gpu_fermat.py).
-// One CTA works on (element e, 256 focal points) items; the lens samples and the element's
-// |A_e - P_j|/c1 row are staged in shared memory and broadcast to the 256 threads.
-// =====================================================================================
-constexpr int kFermatThreads = 256;
-
-struct FermatArgs {
-    const double *fx, *fz;   // [F] focal points
-    long long F;
-    const double *d1;        // [E][N]  |A_e - P_j| / c1
-    const double *alpha;     // [N]
-    double *tof;             // [E][F]
-    int *kmin;               // [E][F]
-    double *alpha_out;       // [E][F] or null
-    double z_el;             // array line
-    unsigned long long *counter;
-};
-
-__global__ void tofrt_fermat_d1_kernel(DevSetup S, double z_el, double *d1)
-{
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int e = blockIdx.y;
-    if (j >= S.K) return;
-    double2 p = S.lens[j];
-    d1[(size_t)e * S.K + j] = dist2d(S.x_rx[e], z_el, p.x, p.y) / S.c1;
-}
-
-// t(alpha) and dt/dalpha at a continuous lens angle
-__device__ __forceinline__ void fermat_eval(const DevSetup &S, double al, double ax, double az, double fx, double fz,
-                                            double *t, double *dt)
-{
-    double sn, cs, h, dz, dx;
-    tofrt_sincos(al, &sn, &cs);
-    lens_point(S, sn, cs, &h, &dz, &dx);
-    double px = h * sn, pz = h * cs;
-    double u1x = px - ax, u1z = pz - az, u2x = px - fx, u2z = pz - fz;
-    double r1 = sqrt(u1x * u1x + u1z * u1z), r2 = sqrt(u2x * u2x + u2z * u2z);
-    *t = r1 / S.c1 + r2 / S.c2;
-    *dt = (u1x * dx + u1z * dz) / (S.c1 * r1) + (u2x * dx + u2z * dz) / (S.c2 * r2);
-}
-
-__global__ void __launch_bounds__(kFermatThreads) tofrt_fermat_kernel(DevSetup S, FermatArgs A)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = S.K;
-    double2 *s_lens = reinterpret_cast<double2 *>(smem_raw);
-    double *s_d1 = reinterpret_cast<double *>(s_lens + N);
-    float2 *s_lens32 = reinterpret_cast<float2 *>(s_d1 + N);  // float copies for the screening pass
-    float *s_d132 = reinterpret_cast<float *>(s_lens32 + N);
-    __shared__ unsigned long long s_item;
-    __shared__ float s_d1max;
-    for (int i = threadIdx.x; i < N; i += kFermatThreads) {
-        const double2 p = S.lens[i];
-        s_lens[i] = p;
-        s_lens32[i] = make_float2((float)p.x, (float)p.y);
-    }
-    const long long tiles = (A.F + kFermatThreads - 1) / kFermatThreads;
-    const unsigned long long items = (unsigned long long)tiles * S.E;
-    const double inv_c2 = 1.0 / S.c2;
-    int cur_e = -1;
-    for (;;) {
-        __syncthreads();  // previous item done with s_d1 / s_item
-        if (threadIdx.x == 0) s_item = atomicAdd(A.counter, 1ull);
-        __syncthreads();
-        const unsigned long long item = s_item;
-        if (item >= items) break;
-        const int e = (int)(item / tiles);
-        const long long f = (long long)(item % tiles) * kFermatThreads + threadIdx.x;
-        if (e != cur_e) {  // uniform across the CTA
-            if (threadIdx.x == 0) s_d1max = 0.f;
-            __syncthreads();
-            float mx = 0.f;
-            for (int i = threadIdx.x; i < N; i += kFermatThreads) {
-                const double v = A.d1[(size_t)e * N + i];
-                s_d1[i] = v;
-                s_d132[i] = (float)v;
-                mx = fmaxf(mx, (float)fabs(v));
-            }
-            atomicMax(reinterpret_cast<int *>(&s_d1max), __float_as_int(mx));  // non-negative floats order as ints
-            cur_e = e;
-            __syncthreads();
-        }
-        if (f >= A.F) continue;
-        const double fx = A.fx[f], fz = A.fz[f];
-        const double ax = S.x_rx[e], az = A.z_el;
-        // ---- discrete argmin over the sampled surface (first minimum on ties) ----
-        // Exact FP64 argmin, found with an FP32 screening pass: t32_j differs from t_j by less than
-        // delta = 2^-19 (D/c2 + max_j d1_j), D = X + Z + |fx| + |fz| (float rounding of the four
-        // coordinates, of the squared distance, the approximate square root and the fma; >2.5x margin),
-        // so the exact minimiser is among the samples with t32_j <= min_j t32_j + 2 delta -- a handful
-        // around the minimum -- and only those are evaluated in FP64, in index order.
-        double best = INFINITY;
-        int jbest = 0;
-        {
-            const float fx32 = (float)fx, fz32 = (float)fz, ic2 = (float)inv_c2;
-            float min32 = INFINITY;
-#pragma unroll 4
-            for (int j = 0; j < N; ++j) {
-                const float2 p = s_lens32[j];
-                const float ux = p.x - fx32, uz = p.y - fz32;
-                min32 = fminf(min32, fmaf(fsqrt_fast(fmaf(ux, ux, uz * uz)), ic2, s_d132[j]));
-            }
-            const float D = (float)(S.X + S.Z + fabs(fx) + fabs(fz));
-            const float thr = min32 + 2.0f * 1.9073486328125e-06f * (D * ic2 + s_d1max) * 1.0001f;
-            const bool screened = thr == thr && thr < INFINITY;  // non-finite inputs: evaluate everything exactly
-#pragma unroll 2
-            for (int j = 0; j < N; ++j) {
-                const float2 p = s_lens32[j];
-                const float ux32 = p.x - fx32, uz32 = p.y - fz32;
-                const float t32 = fmaf(fsqrt_fast(fmaf(ux32, ux32, uz32 * uz32)), ic2, s_d132[j]);
-                if (!screened || t32 <= thr) {
-                    const double2 q = s_lens[j];
-                    const double ux = q.x - fx, uz = q.y - fz;
-                    const double t = fma(sqrt(fma(ux, ux, uz * uz)), inv_c2, s_d1[j]);
-                    if (t < best) { best = t; jbest = j; }
-                }
-            }
-        }
-        // ---- continuous refinement between the neighbouring samples ----
-        double a = A.alpha[max(jbest - 1, 0)], b = A.alpha[min(jbest + 1, N - 1)];
-        double ta, ga, tb, gb, tc, gc;
-        fermat_eval(S, a, ax, az, fx, fz, &ta, &ga);
-        fermat_eval(S, b, ax, az, fx, fz, &tb, &gb);
-        double al = A.alpha[jbest], tof;
-        fermat_eval(S, al, ax, az, fx, fz, &tof, &gc);
-        if (ga < 0.0 && gb > 0.0) {  // a bracketed stationary point: Illinois false position on dt/dalpha
-            int side = 0;
-            for (int it = 0; it < 8; ++it) {
-                double c = (a * gb - b * ga) / (gb - ga);
-                if (!(c > a && c < b)) c = 0.5 * (a + b);
-                fermat_eval(S, c, ax, az, fx, fz, &tc, &gc);
-                al = c; tof = tc;
-                if (gc == 0.0) break;
-                if (gc > 0.0) { b = c; gb = gc; if (side == 1) ga *= 0.5; side = 1; }
-                else { a = c; ga = gc; if (side == -1) gb *= 0.5; side = -1; }
-            }
-        }
-        const size_t o = (size_t)e * A.F + f;
-        A.tof[o] = tof;
-        A.kmin[o] = jbest;
-        if (A.alpha_out) A.alpha_out[o] = al;
-    }
-}
-
-// =====================================================================================
-// 3-D two-point Fermat solve (SURVEY.md row f4 / BASELINE config 5: matrix array, 3-D volume,
-// curved surface).  The reference is 2-D: parity unpinned.  The lens is the surface of revolution
-// of the reference's profile h(alpha); the per-pair arithmetic lives in tofrt_fermat3d.h (shared
-// with the oracle's twin).  For every (matrix-array element e, voxel F) pair:
-//   1. discrete search over a coarse n_side x n_side grid of surface samples: one thread per pair,
-//      the element's (P_s, |A_e - P_s|/c1) table broadcast from shared memory, FP32 arithmetic
-//      (the argmin only selects the start of step 2);
-//   2. projected Newton refinement in FP64, state in registers.
-// One CTA works on (element, 256 voxels) items; outputs are element-major tof[e][f] so a CTA
-// writes 2 KB runs.
-// =====================================================================================
-constexpr int kF3dThreads = 256;
-#ifndef TOFRT_F3D_MIN_BLOCKS
-#define TOFRT_F3D_MIN_BLOCKS 3
-#endif
-
-struct F3dArgs {
-    const double *fx, *fy, *fz;  // [F] voxels
-    long long F;
-    const float4 *smp;           // [E][ns] (P_s.x, P_s.y, P_s.z, |A_e - P_s| / c1)
-    const double *ang;           // [n_side]
-    const double *ex, *ey;       // [E] element positions on the plane z = z_el
-    int E, n_side;
-    double z_el, cell;
-    double *tof;                 // [E][F]
-    int *kmin;                   // [E][F] or null
-    double *ab;                  // [E][F][2] or null
-    unsigned long long *counter;
-};
-
-__global__ void tofrt_f3d_prepare_kernel(tofrt_surf3d S, F3dArgs A, float4 *smp)
-{
-    const int ns = A.n_side * A.n_side;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x, e = blockIdx.y;
-    if (s >= ns) return;
-    double P[3];
-    tofrt_f3d_point(&S, A.ang[s / A.n_side], A.ang[s % A.n_side], P);
-    const double ux = P[0] - A.ex[e], uy = P[1] - A.ey[e], uz = P[2] - A.z_el;
-    const double d1 = sqrt(ux * ux + uz * uz + uy * uy) * S.inv_c1;
-    smp[(size_t)e * ns + s] = make_float4((float)P[0], (float)P[1], (float)P[2], (float)d1);
-}
-
-__global__ void __launch_bounds__(kF3dThreads, TOFRT_F3D_MIN_BLOCKS) tofrt_fermat3d_kernel(tofrt_surf3d S, F3dArgs A)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *s_smp = reinterpret_cast<float4 *>(smem_raw);
-    const int ns = A.n_side * A.n_side;
-    const long long tiles = (A.F + kF3dThreads - 1) / kF3dThreads;
-    const unsigned long long items = (unsigned long long)tiles * A.E;
-    const float ic2 = (float)S.inv_c2;
-    int cur_e = -1;
-    // Dynamic work counter, one (element, 256 voxels) item at a time.  (Dealing the items round-robin
-    // without the two barriers measured 4 % slower: the barrier keeps a CTA's warps in step.)
-    __shared__ unsigned long long s_item;
-    for (;;) {
-        __syncthreads();  // previous item done with s_smp / s_item
-        if (threadIdx.x == 0) s_item = atomicAdd(A.counter, 1ull);
-        __syncthreads();
-        const unsigned long long item = s_item;
-        if (item >= items) break;
-        const int e = (int)(item / tiles);
-        const long long f = (long long)(item % tiles) * kF3dThreads + threadIdx.x;
-        if (e != cur_e) {  // uniform across the CTA; items are element-major, so this is rare
-            for (int i = threadIdx.x; i < ns; i += kF3dThreads) s_smp[i] = A.smp[(size_t)e * ns + i];
-            cur_e = e;
-            __syncthreads();
-        }
-        if (f >= A.F) continue;
-        const double Fp[3] = {A.fx[f], A.fy[f], A.fz[f]};
-        const double Ap[3] = {A.ex[e], A.ey[e], A.z_el};
-        // ---- discrete search over the sampled surface (first minimum on ties) ----
-        int kb = 0;
-        {
-            const float gx = (float)Fp[0], gy = (float)Fp[1], gz = (float)Fp[2];
-            float best = INFINITY;
-#pragma unroll 4
-            for (int s = 0; s < ns; ++s) {
-                const float4 p = s_smp[s];
-                const float ux = p.x - gx, uy = p.y - gy, uz = p.z - gz;
-                const float t = fmaf(fsqrt_fast_ftz(fmaf(ux, ux, fmaf(uy, uy, uz * uz))), ic2, p.w);
-                const bool lt = t < best;
-                best = lt ? t : best;
-                kb = lt ? s : kb;
-            }
-        }
-        // ---- continuous refinement ----
-        const int ia = kb / A.n_side, ib = kb - ia * A.n_side;
-        double t, a, b;
-        tofrt_f3d_refine(&S, A.ang[ia], A.ang[ib], A.cell, Ap, Fp, &t, &a, &b);
-        const size_t o = (size_t)e * A.F + f;
-        A.tof[o] = t;
-        if (A.kmin) A.kmin[o] = kb;
-        if (A.ab) reinterpret_cast<double2 *>(A.ab)[o] = make_double2(a, b);
-    }
-}
-
-// ---- sparse form of the table: only the hits, ordered by (row, receiver) -------------------
-// 97-98 % of the table entries are misses; a consumer on the host that only wants the hits gets
-// them as a list, which cuts the device->host traffic ~30x (the dense D2H is what limits the
-// end-to-end rate once 8 GPUs share the host's PCIe/memory bandwidth).  Deterministic: count per
-// row, exclusive scan, ordered compaction (no atomics).
-__global__ void tofrt_count_hits_kernel(const int *k_hit, long long rows, int E, long long *cnt)
-{
-    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    int n = 0;
-    for (int e = lane; e < E; e += 32) n += k_hit[row * E + e] >= 0;
-    n = __reduce_add_sync(0xffffffffu, n);
-    if (lane == 0) cnt[row] = n;
-}
-
-__global__ void tofrt_compact_hits_kernel(const int *k_hit, const double *tof, long long rows, int E,
-                                          const long long *off, long long row0, long long base, long long capacity,
-                                          int *hit_g, int *hit_e, int *hit_k, double *hit_tof)
-{
-    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    long long o = base + off[row];
-    for (int e0 = 0; e0 < E; e0 += 32) {
-        const int e = e0 + lane;
-        const int kh = e < E ? k_hit[row * E + e] : -1;
-        const unsigned m = __ballot_sync(0xffffffffu, kh >= 0);
-        if (kh >= 0) {
-            const long long i = o + __popc(m & ((1u << lane) - 1u));
-            if (i < capacity) {
-                hit_g[i] = (int)(row0 + row); hit_e[i] = e; hit_k[i] = kh; hit_tof[i] = tof[row * E + e];
-            }
-        }
-        o += __popc(m);
-    }
-}
-
-// ---- FP64 issue-rate micro-benchmark (the roofline denominator, measured on the box) ----
-// 8 independent dependency chains per thread; MODE 0: DFMA, MODE 1: DMUL+DADD (un-fused, as
-// the scan issues them).  Each loop iteration issues 16 FP64 instructions per thread.
-template <int MODE>
-__global__ void __launch_bounds__(256) tofrt_fp64_peak_kernel(double *out, int iters, double a, double b)
-{
-    double v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (double)(threadIdx.x + i) * 1e-3;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (MODE == 0) { v[i] = fma(v[i], a, b); v[i] = fma(v[i], a, b); }
-            else { v[i] = __dmul_rn(v[i], a); v[i] = __dadd_rn(v[i], b); }
-        }
-    }
-    double s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += v[i];
-    if (s == 12345.678) out[0] = s;  // keep the chains alive
-}
+#include "tofrt_common.cuh"
+#include "tofrt_setup_kernels.cuh"
+#include "tofrt_table_kernel.cuh"
+#include "tofrt_table_f32.cuh"
+#include "tofrt_fermat_kernels.cuh"
+#include "tofrt_misc_kernels.cuh"
 
 // ---- host side ----------------------------------------------------------------------
 

@@ -4,7 +4,7 @@
  * sin, cos, tan, atan, atan2, asin (and sincos-of-atan2) built only from IEEE-754 operations that
  * are correctly rounded on every target (+, -, *, /, sqrt, fma), so the very
  * same source gives bit-identical results when compiled
- *   - by nvcc for sm_100a (the product: csrc/tofrt_kernels.cu), and
+ *   - by nvcc for sm_100a (the product: csrc/tofrt_kernels.cu and its .cuh parts), and
  *   - by gcc for the host (the oracle's "device-math" twin, oracle/Makefile),
  * which is what makes GPU-vs-CPU parity of the discrete indices and of the
  * travel times exact instead of "within libm noise".  The reference's own

@@ -1,0 +1,44 @@
+// tofrt_setup_kernels.cuh -- once-per-setup kernels: lens samples, first refraction of every shooter, chords.
+// Part of the single translation unit tofrt_kernels.cu (included inside its anonymous namespace).
+#pragma once
+
+// ---- prepare kernel: main_rt.py:338-349 for every launch angle ----------------
+__global__ void tofrt_prepare_kernel(DevSetup S, const double *alpha, double2 *lens, double *a_pq,
+                                     double *b_pq, double *phi_pq, double *leg1, double *cpq, double *spq, int *bad)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= S.Npad) return;
+    int kk = k < S.K ? k : S.K - 1;  // padding repeats the last sample
+    double al = alpha[kk];
+    double sn, cs, h, dz, dx;
+    tofrt_sincos(al, &sn, &cs);
+    lens_point(S, sn, cs, &h, &dz, &dx);
+    double x_p = h * sn, z_p = h * cs;
+    lens[k] = make_double2(x_p, z_p);
+    if (k >= S.K) return;
+    if (!(fabs(x_p) < 1e150 && fabs(z_p) < 1e150)) atomicOr(bad, 1);
+    for (int s = 0; s < S.n_shooters; ++s) {  // main_rt.py:341-349 for every shooter
+        const double x_sh = S.x_sh[s], z_sh = S.z_sh[s];
+        double phi_ap = tofrt_atan2(z_sh - z_p, x_sh - x_p);
+        double phi = refract(phi_ap, dz, dx, S.c2_over_c1);
+        double a = tofrt_tan(phi);
+        size_t o = (size_t)s * S.K + k;
+        a_pq[o] = a;
+        b_pq[o] = z_p - a * x_p;
+        phi_pq[o] = phi;
+        tofrt_sincos(phi, &spq[o], &cpq[o]);
+        leg1[o] = dist2d(x_sh, z_sh, x_p, z_p) / S.c1;
+    }
+}
+
+// chords of the sampled lens, main_rt.py:127-128 (geometry-independent, so computed once)
+__global__ void tofrt_chord_kernel(int K, const double2 *lens, double2 *seg)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= K - 1) return;
+    double2 p1 = lens[j], p2 = lens[j + 1];
+    double m_seg = (p2.y - p1.y) / (p2.x - p1.x);
+    double b_seg = p1.y - m_seg * p1.x;
+    seg[j] = make_double2(m_seg, b_seg);
+}
+

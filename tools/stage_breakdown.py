@@ -6,7 +6,8 @@ chain of call sites; the outermost call site inside the kernel decides the stage
 
     python tools/stage_breakdown.py gpurun_out/prof.ncu-rep tofrt_table_kernelILb0ELb1ELb0 [out.json]
 
-Stages are cut at marker comments of csrc/tofrt_kernels.cu (MARKERS below)."""
+Stages are cut at marker comments of the kernel's source file (csrc/tofrt_table_kernel.cuh,
+csrc/tofrt_fermat_kernels.cuh; MARKERS below)."""
 import csv
 import io
 import json
@@ -17,7 +18,8 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "ray_tracing_ultrasound_b200", "csrc", "tofrt_kernels.cu")
+CSRC = os.path.join(ROOT, "ray_tracing_ultrasound_b200", "csrc")
+SRC_OF = {"tofrt_table_kernel": "tofrt_table_kernel.cuh", "tofrt_fermat3d_kernel": "tofrt_fermat_kernels.cuh"}
 LIB = os.path.join(ROOT, "ray_tracing_ultrasound_b200", "libtofrt.so")
 
 # (marker text that starts a stage, stage name); searched in order inside the kernel body
@@ -46,8 +48,12 @@ MARKERS = {
 FP64 = re.compile(r"^(D[A-Z]+|MUFU\.(RCP|RSQ)64H)")
 
 
+def source_file(kernel):
+    return SRC_OF[next(k for k in MARKERS if k in kernel)]
+
+
 def stage_table(kernel):
-    text = open(SRC).read()
+    text = open(os.path.join(CSRC, source_file(kernel))).read()
     key = next(k for k in MARKERS if k in kernel)
     start = text.index(MARKERS[key][0][0])
     cuts, pos = [], start
@@ -98,15 +104,16 @@ def main():
     if len(dis) != len(smp):
         sys.exit(f"instruction count differs: nvdisasm {len(dis)} vs capture {len(smp)} -- the capture is of another build")
     cuts = stage_table(kernel)
+    src_name = source_file(kernel)
     agg, tot_s, tot_i = {name: [0, 0, 0] for _, name in cuts}, 0, 0
     unknown = [0, 0]
     for (off, op, line), (_, ns, ni) in zip(dis, smp):
         name = None
-        if line and os.path.basename(line[0]) == "tofrt_kernels.cu":
+        if line and os.path.basename(line[0]) == src_name:
             for ln, nm in cuts:
                 if line[1] >= ln:
                     name = nm
-        if name is None and line and os.path.basename(line[0]) == "tofrt_kernels.cu":
+        if name is None and line and os.path.basename(line[0]).startswith("tofrt_"):
             name = "out-of-line helpers (scan_exact_from)"
             agg.setdefault(name, [0, 0, 0])
         if name is None:
