@@ -66,3 +66,25 @@ def test_twin_plane_y0_is_the_2d_problem(oracle_dm):
             r = minimize_scalar(lambda al: lens.tof(al, ex[e], float(rs.D), fx[f], fz[f]) * 1e4,
                                 bounds=(-rs.ALPHA_MAX, rs.ALPHA_MAX), method="bounded", options=dict(xatol=1e-12))
             assert abs(tof[e, f] - r.fun * 1e-4) < 1e-17
+
+
+def test_twin_flat_interface_known_answer(oracle_dm):
+    """Flat interface z = h0 in 3-D: for a voxel straight below an element the entry point is straight above it and
+    the time is (d - h0)/c1 + (h0 - z)/c2; off-axis pairs obey Snell's law (gradient zero at the entry point)."""
+    p = oracle_dm.params()
+    ang = _ang(17)
+    rng = np.random.default_rng(4)
+    ex, ey = rng.uniform(-0.009, 0.009, 8), rng.uniform(-0.009, 0.009, 8)
+    fz = rng.uniform(0.0, 0.05, 8)
+    try:
+        oracle_dm.set_surface(True)
+        tof, kmin, ab, evals, gap = oracle_dm.fermat3d(p, ang, ex, ey, float(rs.D), ex, ey, fz)
+        straight = (float(rs.D) - float(rs.H0)) / float(rs.C1) + (float(rs.H0) - fz) / float(rs.C2)
+        assert np.abs(np.diag(tof) - straight).max() < 1e-18
+        for e in range(8):
+            for f in range(8):
+                _, g, H = oracle_dm.fermat3d_eval(p, ang, ab[e, f, 0], ab[e, f, 1], (ex[e], ey[e], float(rs.D)),
+                                                  (ex[f], ey[f], fz[f]))
+                assert np.abs(g).max() < 1e-15 and H[0] > 0 and H[0] * H[2] - H[1] ** 2 > 0
+    finally:
+        oracle_dm.set_surface(False)
