@@ -13,6 +13,9 @@
  * conventions are the reference's: atan in (-pi/2, pi/2] for the pipe slope, principal asin
  * (cos(theta_2) >= 0), NaN on total internal reflection and where sqrt(r^2 - x_q^2) is not real.
  *
+ * Range: the reflected direction is carried scaled by r^2, so radii beyond ~1e150 m overflow here where the
+ * angle form would still return a finite slope (TOFRT_MATH_ANGLE remains available for such inputs).
+ *
  * Shared bit for bit between nvcc (the kernel) and gcc (the oracle's device-math twin, which
  * switches to these functions with tofo_set_math(1)).  IEEE operations only; fused operations are
  * explicit fma() calls.
