@@ -68,3 +68,36 @@ def test_vector_form_per_ray_nan_pattern(oracle_dm):
         if ok.any():   # landing points agree to ~1e-13 of their size (1 mm floor): nothing near the 1e-6 m hit tolerance
             err = np.abs(a["target_x"] - b["target_x"])[ok] / np.maximum(np.abs(a["target_x"][ok]), 1e-3)
             assert err.max() < 2e-12
+
+
+def test_vector_form_other_materials_and_lenses(oracle_dm, oracle_libm):
+    """Random wave speeds, lens dimensions, ray counts, arrays, shooters and tolerances (the parameter space of
+    tools/fuzz_parity.py): the vector form keeps the hit decisions of the libm oracle (reference operation order)."""
+    n_hits = 0
+    for i in range(8):
+        r4 = np.random.default_rng(7000 + i)
+        kw = dict(c1=r4.uniform(3000, 7000), c2=r4.uniform(900, 2500), l0=r4.uniform(0.05, 0.2), h0=r4.uniform(0.04, 0.12))
+        K = int(r4.integers(64, 700))
+        nel = int(r4.choice([16, 64, 128]))
+        d = float(np.float64(kw["l0"]) + np.float64(kw["h0"]))
+        xa, _ = rs.transducer(num_elements=nel, pitch=np.float64(r4.uniform(2e-4, 8e-4)), d=d)
+        al = np.linspace(-r4.uniform(0.3, 0.85), r4.uniform(0.3, 0.85), K)
+        zf = np.ones(K) * d
+        sh = int(r4.integers(0, len(xa)))
+        rtol, atol = 10.0 ** r4.uniform(-7, -4), 10.0 ** r4.uniform(-6, -4)
+        radii, offsets = r4.uniform(0.05, 1.1, 250) * kw["h0"], r4.uniform(-0.3, 0.3, 250) * kw["h0"]
+        p = oracle_dm.params(**kw)
+        args = (p, radii, offsets, xa[sh], d, zf, al, xa)
+        try:
+            oracle_dm.set_math(True)
+            t1, k1, i1 = oracle_dm.table(*args, rtol=rtol, atol=atol, want_idx=True)
+        finally:
+            oracle_dm.set_math(False)
+        tl, kl, il = oracle_libm.table(*args, rtol=rtol, atol=atol, want_idx=True)
+        assert np.array_equal(k1, kl), i
+        hit = k1 >= 0
+        n_hits += int(hit.sum())
+        if hit.any():
+            assert np.abs(t1 - tl)[hit].max() < 1e-12
+        assert (i1 != il).mean() < 2e-3      # the index only differs where the decision is rounding noise
+    assert n_hits > 1000
