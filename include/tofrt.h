@@ -134,10 +134,19 @@ int tofrt_set_option(tofrt_ctx *ctx, int option, int value);
 #define TOFRT_INFO_MATH 3
 int tofrt_get_info(tofrt_ctx *ctx, int what);
 
-/* Search statistics of the most recent table call on this context (synchronises):
- * [0] rays traced, [1] rays whose index needed the O(N) scan, [2] 32-ray groups that
- * ran the scan loop, [3] rays that needed the |diff| <= 1e-8 on-sample pass. */
-int tofrt_last_stats(tofrt_ctx *ctx, unsigned long long *stats4);
+/* Executed-work statistics.  tofrt_set_option(ctx, TOFRT_OPT_STATS, 1) makes the following table calls run the
+ * INSTRUMENTED instantiation of the table kernel (same results; a few percent slower -- leave it off when timing);
+ * tofrt_last_stats then returns the counters of the most recent table call on this context (synchronises), counted
+ * per thread-ray (a warp walks 32 * ceil(K / 32) rays per geometry: indices beyond K-1 repeat the last ray):
+ * [0] rays traced, [1] rays whose return path got a certified bracket (guided search), [2] bracket probes,
+ * [3] exact diffs of main_rt.py:78 evaluated (bracket check or literal scan), [4] rays that entered the lens again,
+ * [5] rays that reached the array line (no total internal reflection), [6] np.isclose receiver tests, [7] rays that
+ * won a receiver (four legs computed), [8] rays that needed the fallback bisection, [9] rays that needed the exact
+ * O(N) scan (guided mode: undecidable rays; 0 in every run so far), [10] rays that ran the |diff| <= 1e-8 on-sample rule.
+ * Entries beyond TOFRT_NUM_STATS are zero.  With statistics off the counters read zero. */
+#define TOFRT_OPT_STATS 4
+#define TOFRT_NUM_STATS 11
+int tofrt_last_stats(tofrt_ctx *ctx, unsigned long long *stats, int n);
 
 /* Lens samples of the current setup, "lens_1_x"/"lens_1_z" (main_rt.py:338). */
 int tofrt_lens_host(tofrt_ctx *ctx, double *lens_x, double *lens_z);

@@ -84,14 +84,16 @@ class Oracle:
         out = {k: np.empty(n) for k in ("lens_1_x", "lens_1_z", "pipe_x", "pipe_z", "lens_2_x",
                                         "lens_2_z", "target_x", "target_z", "a_l", "b_l")}
         idx = np.empty(n, dtype=np.int32)
+        margin = np.empty(n)
         rc = self.lib.tofo_shoot_rays(
             ctypes.byref(p), ctypes.c_double(r_outer), ctypes.c_double(pipe_offset),
             ctypes.c_double(x_a), ctypes.c_double(z_a), _dp(z_f), _dp(alpha), ctypes.c_int(n),
             _dp(out["lens_1_x"]), _dp(out["lens_1_z"]), ctypes.c_int(0),
             _dp(out["pipe_x"]), _dp(out["pipe_z"]), _dp(out["lens_2_x"]), _dp(out["lens_2_z"]),
-            _dp(out["target_x"]), _dp(out["target_z"]), _ip(idx), _dp(out["a_l"]), _dp(out["b_l"]))
+            _dp(out["target_x"]), _dp(out["target_z"]), _ip(idx), _dp(out["a_l"]), _dp(out["b_l"]), _dp(margin))
         assert rc == 0, rc
         out["idx"] = idx
+        out["margin"] = margin
         return out
 
     def ray_legs(self, p, x_a, z_a, res):
@@ -106,21 +108,24 @@ class Oracle:
         return legs
 
     def table(self, p, radius, offset, x_a, z_a, z_f, alpha, x_rx, rtol=1e-5, atol=1e-6,
-              want_idx=False, nthreads=0):
-        """main_rt.py:464-501 -> (tof[E][G], k_hit[E][G], idx[G][n] or None)."""
+              want_idx=False, nthreads=0, want_margin=False):
+        """main_rt.py:464-501 -> (tof[E][G], k_hit[E][G], idx[G][n] or None[, margin[G][n]]).
+        margin: how far each ray's return-path decision is from rounding noise (min |diff| at the first sign
+        change, or over all samples when there is none; NaN for NaN lines)."""
         radius, offset, z_f, alpha, x_rx = map(_f64, (radius, offset, z_f, alpha, x_rx))
         G, n, E = len(radius), len(alpha), len(x_rx)
         assert len(offset) == G and len(z_f) == n
         tof = np.empty((E, G))
         k_hit = np.empty((E, G), dtype=np.int32)
         idx = np.empty((G, n), dtype=np.int32) if want_idx else None
+        margin = np.empty((G, n)) if want_margin else None
         rc = self.lib.tofo_table(
             ctypes.byref(p), _dp(radius), _dp(offset), ctypes.c_int(G), ctypes.c_double(x_a),
             ctypes.c_double(z_a), _dp(z_f), _dp(alpha), ctypes.c_int(n), _dp(x_rx), ctypes.c_int(E),
             ctypes.c_double(rtol), ctypes.c_double(atol), _dp(tof), _ip(k_hit), _ip(idx),
-            ctypes.c_int(nthreads))
+            _dp(margin) if want_margin else None, ctypes.c_int(nthreads))
         assert rc == 0, rc
-        return tof, k_hit, idx
+        return (tof, k_hit, idx, margin) if want_margin else (tof, k_hit, idx)
 
     # ---- 3-D two-point Fermat solve: CPU twin of the CUDA kernel (device-math build only) ----
     def fermat3d(self, p, ang, ex, ey, z_el, fx, fy, fz):

@@ -59,7 +59,7 @@ def load():
                                          ctypes.c_int, ctypes.c_double, ctypes.c_double]
     lib.tofrt_set_option.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     lib.tofrt_get_info.argtypes = [ctypes.c_void_p, ctypes.c_int]
-    lib.tofrt_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]
+    lib.tofrt_last_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
     lib.tofrt_lens_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.tofrt_table_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(RayRecords), ctypes.c_void_p]

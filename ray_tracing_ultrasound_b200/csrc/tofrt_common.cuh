@@ -24,6 +24,11 @@ constexpr int kThreadsGuided = TOFRT_THREADS_GUIDED;
 #endif
 constexpr int kChunk = TOFRT_SCAN_CHUNK;  // lens samples per early-exit check of the literal scan (<= 32)
 constexpr int kNoHit = 0x7fffffff;
+// transposed per-ray tables of the FP64 table kernel: ray_t[shooter][plane][c][lane] holds ray min(lane*C + c, K-1)
+enum { kPlaneXp, kPlaneZp, kPlaneCpq, kPlaneSpq, kPlaneZf, kPlaneApq, kPlaneBpq, kPlanePhi, kRayPlanes };
+// executed-work counters of the instrumented (STATS) instantiation, per thread-ray (tofrt_last_stats)
+enum { kStRays, kStBracket, kStProbes, kStDiffs, kStLens2, kStLanding, kStCand, kStWinners, kStFallback, kStScan,
+       kStOnSample, kNumStats };
 #ifndef TOFRT_CHUNK_MB
 #define TOFRT_CHUNK_MB 64  // output bytes per pipelined chunk of tofrt_table_host
 #endif
@@ -34,11 +39,16 @@ struct DevSetup {
     double c1, c2, d;
     double A, fourAC, twoA, twod, K2, phi1;  // lens surface (main_rt.py:181-212)
     double c2_over_c1, c1_over_c2;           // v2 / v1 of the two refractions
+    tofrt_vec_lens VL;                       // the same constants as the vector form uses them (tofrt_raymath.h)
     int n_shooters;                          // S: shots per geometry (full-matrix capture when S = E)
     const double *x_sh, *z_sh;               // [S] shooter positions
     double rtol, atol, tol_max;              // np.isclose tolerances, and an upper bound of atol+rtol|x_e|
     double rx_min, rx_max;                   // finite receiver range
     int K, Npad, E, E_sorted, has_nonfinite_rx, tables_ok;
+    int C;                 // rays per lane of the table kernel: ceil(K / 32)
+    const double *ray_t;   // [S][kRayPlanes][C][32] transposed per-ray tables
+    double2 P0, PN;        // first and last lens sample (the guided search tests them for every ray)
+    int chords_plain;    // 1: abscissae strictly increasing and no chord is np.isclose-vertical (main_rt.py:110): checked per setup
     int hits_in_global;  // 1: E too large for the per-warp shared-memory first-hit state -> keep it in the output rows
     int shape;      // +1: sampled lens strictly concave in x, -1: strictly convex, 0: neither (no guided search)
     int guided;     // search mode: 1 = guided (bracketed) search, 0 = the reference's literal O(N) scan
@@ -55,7 +65,8 @@ struct DevSetup {
     const double *x_rx;    // [E] as given
     const double *xs;      // [E_sorted] finite receivers, ascending
     const int *perm;       // [E_sorted] original index of xs[i]
-    // candidate lookup: bucket[c] = first i with xs[i] >= bx0 + (c-1)/binv (one cell of slack), nb cells
+    // candidate lookup: nb cells of width 1/binv from bx0; bucket[c] = first | count << 16 lists the sorted receivers
+    // that a landing point whose computed cell index is c can match (one cell of slack either side + tol_max)
     const int *bucket;
     int nb;
     double bx0, binv;
@@ -71,7 +82,7 @@ struct TableArgs {
     int s_begin, s_count;  // shooters [s_begin, s_begin + s_count) of the setup; outputs are [s_count][G][...]
     const double *inject_m, *inject_b;  // test hook (tofrt_debug_search_host): replace the reflected line of ray [w][k]
     unsigned long long *counter;
-    unsigned long long *stats;  // [4]: rays traced, rays that needed the O(N) scan, warp-chunks that ran it, on-sample passes
+    unsigned long long *stats;  // [kNumStats] executed-work counters (instrumented instantiation only)
 };
 
 // ---- small device helpers ---------------------------------------------------

@@ -42,6 +42,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <type_traits>
 #include <string>
 #include <vector>
@@ -73,16 +74,21 @@ int fail(int code, const std::string &msg)
 }
 
 typedef void (*table_kernel_t)(DevSetup, TableArgs);
-// the instantiation for (first-hit state in global memory, guided search, flat surface, vector math)
-table_kernel_t pick_table_kernel(bool hg, bool guided, bool flat, bool vec)
+// the instantiation for (first-hit state in global memory, guided search, flat surface, vector math); `stats` selects
+// the instrumented twin (shared-memory first-hit state, lens surface only)
+table_kernel_t pick_table_kernel(bool hg, bool guided, bool flat, bool vec, bool stats = false)
 {
-    if (flat) return vec ? tofrt_table_kernel<false, false, true, true> : tofrt_table_kernel<false, false, true, false>;
-    if (hg) {
-        if (guided) return vec ? tofrt_table_kernel<true, true, false, true> : tofrt_table_kernel<true, true, false, false>;
-        return vec ? tofrt_table_kernel<true, false, false, true> : tofrt_table_kernel<true, false, false, false>;
+    if (stats && !flat && !hg) {
+        if (guided) return vec ? tofrt_table_kernel<false, true, false, true, true> : tofrt_table_kernel<false, true, false, false, true>;
+        return vec ? tofrt_table_kernel<false, false, false, true, true> : tofrt_table_kernel<false, false, false, false, true>;
     }
-    if (guided) return vec ? tofrt_table_kernel<false, true, false, true> : tofrt_table_kernel<false, true, false, false>;
-    return vec ? tofrt_table_kernel<false, false, false, true> : tofrt_table_kernel<false, false, false, false>;
+    if (flat) return vec ? tofrt_table_kernel<false, false, true, true, false> : tofrt_table_kernel<false, false, true, false, false>;
+    if (hg) {
+        if (guided) return vec ? tofrt_table_kernel<true, true, false, true, false> : tofrt_table_kernel<true, true, false, false, false>;
+        return vec ? tofrt_table_kernel<true, false, false, true, false> : tofrt_table_kernel<true, false, false, false, false>;
+    }
+    if (guided) return vec ? tofrt_table_kernel<false, true, false, true, false> : tofrt_table_kernel<false, true, false, false, false>;
+    return vec ? tofrt_table_kernel<false, false, false, true, false> : tofrt_table_kernel<false, false, false, false, false>;
 }
 
 #define CUDA_TRY(expr)                                                                        \
@@ -93,6 +99,12 @@ table_kernel_t pick_table_kernel(bool hg, bool guided, bool flat, bool vec)
     } while (0)
 
 }  // namespace
+
+// Largest dynamic shared-memory request of any kernel here (227 KB per CTA minus 1 KB for the kernels' few static
+// variables).  The per-function opt-in attribute is per DEVICE, not per context, so it is always raised to this
+// maximum: two live contexts with different K / E on one GPU can then never lower each other's limit.
+constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;
+constexpr unsigned kCounterSlots = 64, kCounterStride = 16;  // 128 B per slot: [0] work counter, [1..] statistics
 
 struct tofrt_ctx {
     int device = 0;
@@ -106,6 +118,8 @@ struct tofrt_ctx {
     // device buffers owned by the context
     double *d_alpha = nullptr, *d_zf = nullptr, *d_a = nullptr, *d_b = nullptr, *d_phi = nullptr, *d_leg1 = nullptr;
     double *d_cs = nullptr;   // cos / sin of phi_pq, [2][S*K]
+    double *d_ray_t = nullptr;  // transposed per-ray tables of the table kernel
+    int opt_stats = 0;          // 1: table calls run the instrumented instantiation (tofrt_last_stats)
     double2 *d_lens = nullptr, *d_seg = nullptr;
     int opt_guided = 1;
     int opt_surface = 0;
@@ -116,7 +130,18 @@ struct tofrt_ctx {
     double *d_xrx = nullptr, *d_xs = nullptr, *d_sh = nullptr;
     int n_shooters = 1;
     int *d_perm = nullptr, *d_bad = nullptr, *d_bucket = nullptr;
+    // Work counters: every launch draws its own slot (dynamic work counter + statistics) from a ring, zeroed on the
+    // caller's stream, so calls in flight on different streams never share one (up to kCounterSlots at a time).
     unsigned long long *d_counter = nullptr;
+    std::atomic<unsigned> next_slot{0};
+    unsigned last_table_slot = 0;
+    unsigned long long *take_counter(cudaStream_t st, cudaError_t *err)
+    {
+        const unsigned slot = next_slot.fetch_add(1) % kCounterSlots;
+        unsigned long long *p = d_counter + (size_t)slot * kCounterStride;
+        *err = cudaMemsetAsync(p, 0, kCounterStride * sizeof(unsigned long long), st);
+        return p;
+    }
     // host-buffer pipeline (tofrt_table_host)
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -140,6 +165,7 @@ struct tofrt_ctx {
         cudaFree(d_lens); cudaFree(d_seg); cudaFree(d_f32); cudaFree(d_sh); cudaFree(d_xrx); cudaFree(d_xs); cudaFree(d_perm); cudaFree(d_bad);
         cudaFree(d_bucket); d_bucket = nullptr;
         cudaFree(d_cs); d_cs = nullptr;
+        cudaFree(d_ray_t); d_ray_t = nullptr;
         d_alpha = d_zf = d_a = d_b = d_phi = d_leg1 = d_xrx = d_xs = nullptr;
         d_lens = d_seg = nullptr; d_perm = d_bad = nullptr; d_f32 = nullptr; d_sh = nullptr;
     }
@@ -165,7 +191,7 @@ int tofrt_create(tofrt_ctx **out, int device)
     tofrt_ctx *c = new tofrt_ctx();
     c->device = device;
     cudaError_t e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, 5 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counter, (size_t)kCounterSlots * kCounterStride * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&c->d_bad, sizeof(int));
     if (e != cudaSuccess) {
         delete c;
@@ -233,6 +259,9 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     S.c1_over_c2 = p->c1 / p->c2;
     S.n_shooters = NS;
     S.surface = c->opt_surface; S.h0 = p->h0;
+    // tofrt_vec_lens_consts, evaluated on the host (IEEE division: the same bits as on the device)
+    S.VL.twod = S.twod; S.VL.K2 = S.K2; S.VL.fourAC = S.fourAC; S.VL.inv_twoA = 1.0 / S.twoA;
+    S.VL.pt = -(S.phi1 * S.twod); S.VL.k12 = S.c1_over_c2; S.VL.h0 = S.h0; S.VL.flat = S.surface != 0;
     S.rtol = rtol; S.atol = atol;
     S.K = K; S.E = E;
     S.Npad = 1 + ((K - 1 + kChunk - 1) / kChunk) * kChunk;
@@ -256,25 +285,33 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     S.rx_min = xs.empty() ? 1.0 : xs.front();
     S.rx_max = xs.empty() ? -1.0 : xs.back();
 
-    // bucket table for the candidate lookup of the table assembly: nb uniform cells over the finite
-    // receiver range (+- tol_max); bucket[c] = first sorted receiver >= start of cell c-1, so a lookup
-    // that is off by one cell through rounding still starts at or before the wanted receiver
+    // Cell table for the candidate lookup of the table assembly: nb uniform cells over the finite receiver range
+    // (+- tol_max, two guard cells at either end).  A landing point t is filed under c = int((t - bx0) * binv),
+    // clamped; the two roundings of that expression move c by at most one cell, so cell c lists every receiver
+    // within tol_max of [start(c-1), end(c+1)]: first | count << 16.  ~16 cells per receiver spacing leave most
+    // cells empty -- a ray that lands between two receivers is dismissed by one shared-memory load.
     std::vector<int> bucket;
     S.nb = 0; S.bx0 = 0.0; S.binv = 0.0;
 #ifndef TOFRT_NO_BUCKET  /* tuning knob: binary search instead */
-    if (S.E_sorted >= 8) {
-        const double x0 = xs.front() - S.tol_max, range = (xs.back() + S.tol_max) - x0;
-        const int nb = std::min(4 * S.E_sorted, 8192);
-        const double cell = range / nb, binv = 1.0 / cell;
-        if (std::isfinite(range) && range > 0.0 && std::isfinite(binv) && cell > 0.0) {
+    if (S.E_sorted >= 1 && S.E_sorted <= 0xffff) {
+        const int nb = std::min(16 * S.E_sorted + 4, 8192);
+        const double lo = xs.front() - S.tol_max, range = (xs.back() + S.tol_max) - lo;
+        const double cell = range > 0.0 ? range / (nb - 4) : 1e-300, binv = 1.0 / cell, x0 = lo - 2 * cell;
+        if (std::isfinite(range) && std::isfinite(binv) && cell > 0.0 && std::isfinite(x0) && nb > 4) {
             bucket.resize(nb);
-            int i = 0;
+            int first = 0, last = 0;
+            bool ok = true;
             for (int cidx = 0; cidx < nb; ++cidx) {
-                const double start = x0 + (cidx - 1) * cell;
-                while (i < S.E_sorted && xs[i] < start) ++i;
-                bucket[cidx] = i;
+                const double from = x0 + (cidx - 1) * cell - S.tol_max, to = x0 + (cidx + 2) * cell + S.tol_max;
+                while (first < S.E_sorted && xs[first] < from) ++first;
+                if (last < first) last = first;
+                while (last < S.E_sorted && xs[last] <= to) ++last;
+                if (last - first > 0xffff) ok = false;
+                bucket[cidx] = first | ((last - first) << 16);
             }
-            S.nb = nb; S.bx0 = x0; S.binv = binv;
+            // the clamped end cells also receive every landing point beyond them: they must stay empty
+            if ((bucket[0] >> 16) != 0 || ((unsigned)bucket[nb - 1] >> 16) != 0) ok = false;
+            if (ok) { S.nb = nb; S.bx0 = x0; S.binv = binv; } else bucket.clear();
         }
     }
 #endif
@@ -283,11 +320,11 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     size_t smem = smem_tables + (size_t)kWarps * E * (sizeof(double) + sizeof(int));
     size_t smem_guided = smem_tables + (size_t)(kThreadsGuided / 32) * E * (sizeof(double) + sizeof(int));
     S.hits_in_global = 0;
-    if (std::max(smem, smem_guided) > 227 * 1024) {  // many receivers: the per-warp first-hit state moves to the output rows
+    if (std::max(smem, smem_guided) > kMaxDynSmem) {  // many receivers: the per-warp first-hit state moves to the output rows
         S.hits_in_global = 1;
         smem = smem_guided = smem_tables;
     }
-    if (smem > 227 * 1024)
+    if (smem > kMaxDynSmem)
         return fail(TOFRT_E_TOOLARGE, "tofrt_setup: K/E need " + std::to_string(smem) + " B of shared memory (> 227 KB)");
 
     CUDA_TRY(cudaMalloc(&c->d_alpha, sizeof(double) * K));
@@ -297,6 +334,9 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     CUDA_TRY(cudaMalloc(&c->d_phi, sizeof(double) * K * NS));
     CUDA_TRY(cudaMalloc(&c->d_leg1, sizeof(double) * K * NS));
     CUDA_TRY(cudaMalloc(&c->d_cs, sizeof(double) * 2 * K * NS));
+    S.C = (K + 31) / 32;
+    CUDA_TRY(cudaMalloc(&c->d_ray_t, sizeof(double) * (size_t)kRayPlanes * S.C * 32 * NS));
+    S.ray_t = c->d_ray_t;
     CUDA_TRY(cudaMalloc(&c->d_lens, sizeof(double2) * S.Npad));
     CUDA_TRY(cudaMalloc(&c->d_seg, sizeof(double2) * K));
     CUDA_TRY(cudaMemset(c->d_seg, 0, sizeof(double2) * K));  // entry K-1 is padding (TMA copies K entries)
@@ -327,6 +367,8 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     CUDA_TRY(cudaGetLastError());
     tofrt_chord_kernel<<<(K + 127) / 128, 128>>>(K, c->d_lens, c->d_seg);
     CUDA_TRY(cudaGetLastError());
+    tofrt_transpose_kernel<<<(unsigned)(((size_t)S.C * 32 * NS + 127) / 128), 128>>>(S, c->d_ray_t);
+    CUDA_TRY(cudaGetLastError());
     int bad = 0;
     CUDA_TRY(cudaMemcpy(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
     S.tables_ok = bad ? 0 : 1;
@@ -337,13 +379,19 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
         std::vector<double2> hl(K), hs(K);
         CUDA_TRY(cudaMemcpy(hl.data(), c->d_lens, sizeof(double2) * K, cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(hs.data(), c->d_seg, sizeof(double2) * (K - 1), cudaMemcpyDeviceToHost));
-        bool incr = true, dec = true, inc = true;
+        bool incr = true, dec = true, inc = true, vertical = false;
         double X = 0, Z = 0;
         for (int j = 0; j < K; ++j) {
             X = std::max(X, std::fabs(hl[j].x));
             Z = std::max(Z, std::fabs(hl[j].y));
             if (j + 1 < K && !(hl[j + 1].x > hl[j].x)) incr = false;
+            if (j + 1 < K) {  // np.isclose(x1, x2) of main_rt.py:110, with b = x2
+                const double x1 = hl[j].x, x2 = hl[j + 1].x;
+                if (((std::fabs(x1 - x2) <= 1e-8 + 1e-5 * std::fabs(x2)) && std::isfinite(x2)) || x1 == x2) vertical = true;
+                if (!(hl[j].y == hl[j].y) || !(hl[j + 1].y == hl[j + 1].y)) vertical = true;  // NaN heights: generic path
+            }
         }
+        S.chords_plain = (S.tables_ok && incr && !vertical) ? 1 : 0;
         for (int j = 0; j + 2 < K; ++j) {
             double a = hs[j].x, b2 = hs[j + 1].x;
             double guard = 16 * 2.220446049250313e-16 * std::max(std::fabs(a), std::fabs(b2));
@@ -351,6 +399,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
             if (!(b2 - a > guard)) inc = false;
         }
         S.X = X; S.Z = Z;
+        S.P0 = hl[0]; S.PN = hl[K - 1];
         S.shape = (S.tables_ok && incr && K >= 3 && S.surface == 0) ? (dec ? 1 : (inc ? -1 : 0)) : 0;
         int lg = 1;
         while ((1 << lg) < K) ++lg;
@@ -389,10 +438,10 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
         c->SF = F;
         c->smem_f32 = (size_t)2 * K * sizeof(float2) + (size_t)S.E_sorted * (sizeof(float) + sizeof(int)) +
                       (size_t)kWarps * E * (sizeof(float) + sizeof(int)) + 16;
-        if (c->smem_f32 > 227 * 1024) c->smem_f32 = 0;  // FP32 mode keeps its first-hit state in shared memory only
+        if (c->smem_f32 > kMaxDynSmem) c->smem_f32 = 0;  // FP32 mode keeps its first-hit state in shared memory only
         else
             CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)c->smem_f32));
+                                          (int)kMaxDynSmem));
         CUDA_TRY(cudaDeviceSynchronize());
     }
 
@@ -401,8 +450,9 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     const bool flat = S.surface != 0, hg = S.hits_in_global != 0;
     for (int vec = 0; vec < 2; ++vec)
         for (int gd = 0; gd < (flat ? 1 : 2); ++gd)
-            CUDA_TRY(cudaFuncSetAttribute(pick_table_kernel(hg, gd != 0, flat, vec != 0),
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(gd ? smem_guided : smem)));
+            for (int stt = 0; stt < 2; ++stt)
+                CUDA_TRY(cudaFuncSetAttribute(pick_table_kernel(hg, gd != 0, flat, vec != 0, stt != 0),
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     int occ = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_table_kernel(hg, !flat, flat, c->opt_vector != 0),
                                                              flat ? kThreads : kThreadsGuided, flat ? smem : smem_guided));
@@ -430,6 +480,11 @@ int tofrt_set_option(tofrt_ctx *c, int option, int value)
         c->S.vector_math = value;
         return TOFRT_OK;
     }
+    if (option == TOFRT_OPT_STATS) {
+        if (value != 0 && value != 1) return fail(TOFRT_E_BADARG, "tofrt_set_option: bad statistics switch");
+        c->opt_stats = value;
+        return TOFRT_OK;
+    }
     if (option == TOFRT_OPT_SURFACE) {
         if (value != TOFRT_SURFACE_LENS && value != TOFRT_SURFACE_FLAT)
             return fail(TOFRT_E_BADARG, "tofrt_set_option: bad surface type");
@@ -440,11 +495,13 @@ int tofrt_set_option(tofrt_ctx *c, int option, int value)
     return fail(TOFRT_E_BADARG, "tofrt_set_option: unknown option");
 }
 
-int tofrt_last_stats(tofrt_ctx *c, unsigned long long *stats4)
+int tofrt_last_stats(tofrt_ctx *c, unsigned long long *stats, int n)
 {
-    if (!c || !stats4) return fail(TOFRT_E_BADARG, "tofrt_last_stats: NULL argument");
+    if (!c || !stats || n < 0) return fail(TOFRT_E_BADARG, "tofrt_last_stats: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaMemcpy(stats4, c->d_counter + 1, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long h[kNumStats];
+    CUDA_TRY(cudaMemcpy(h, c->d_counter + (size_t)c->last_table_slot * kCounterStride + 1, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) stats[i] = i < kNumStats ? h[i] : 0ull;
     return TOFRT_OK;
 }
 
@@ -486,16 +543,18 @@ static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_
     T.any_rec = T.rec.pipe_x || T.rec.pipe_z || T.rec.lens2_x || T.rec.lens2_z || T.rec.target_x || T.rec.idx;
     T.s_begin = s_begin; T.s_count = s_count;
     T.inject_m = inject_m; T.inject_b = inject_b;
-    T.counter = c->d_counter;
-    T.stats = c->d_counter + 1;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
+    cudaError_t ce;
+    T.counter = c->take_counter(st, &ce);
+    CUDA_TRY(ce);
+    T.stats = T.counter + 1;
+    c->last_table_slot = (unsigned)((T.counter - c->d_counter) / kCounterStride);
     long long warps_needed = G * s_count;
     const bool guided = c->S.guided && c->S.shape != 0 && c->S.surface == 0;
     const int threads = guided ? kThreadsGuided : kThreads, wpc = threads / 32;
     const size_t smem = guided ? c->smem_guided : c->smem;
     int grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, (warps_needed + wpc - 1) / wpc);
     // (flat interface, extension: a plane has no strict curvature, so `guided` is false there: literal scan only)
-    pick_table_kernel(c->S.hits_in_global != 0, guided, c->S.surface != 0, c->S.vector_math != 0)
+    pick_table_kernel(c->S.hits_in_global != 0, guided, c->S.surface != 0, c->S.vector_math != 0, c->opt_stats != 0)
         <<<grid, threads, smem, st>>>(c->S, T);
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
@@ -520,8 +579,9 @@ int tofrt_table_f32_dev(tofrt_ctx *c, const double *d_radius, const double *d_of
     TableArgsF T{};
     T.radius = d_radius; T.offset = d_offset; T.G = G; T.tof = d_tof; T.k_hit = d_k_hit;
     T.s_begin = 0; T.s_count = c->n_shooters;
-    T.counter = c->d_counter;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
+    cudaError_t ce;
+    T.counter = c->take_counter(st, &ce);
+    CUDA_TRY(ce);
     int grid = (int)std::min<long long>((long long)c->sm_count, (G * c->n_shooters + kWarps - 1) / kWarps);
     tofrt_table_kernel_f32<<<grid, kThreads, c->smem_f32, st>>>(c->SF, T);
     CUDA_TRY(cudaGetLastError());
@@ -788,18 +848,20 @@ int tofrt_fermat_dev(tofrt_ctx *c, const double *d_fx, const double *d_fz, long 
     cudaStream_t st = (cudaStream_t)stream;
     const int K = c->K, E = c->E;
     const size_t smem = (size_t)K * (sizeof(double2) + sizeof(double) + sizeof(float2) + sizeof(float)) + 16;
-    if (smem > 227 * 1024) return fail(TOFRT_E_TOOLARGE, "tofrt_fermat_dev: too many lens samples");
+    if (smem > kMaxDynSmem) return fail(TOFRT_E_TOOLARGE, "tofrt_fermat_dev: too many lens samples");
     if (!c->d_d1) {
         CUDA_TRY(cudaMalloc(&c->d_d1, sizeof(double) * (size_t)K * E));
         dim3 grid((K + 127) / 128, E);
         tofrt_fermat_d1_kernel<<<grid, 128, 0, st>>>(c->S, c->params_d, c->d_d1);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaFuncSetAttribute(tofrt_fermat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(tofrt_fermat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     }
     FermatArgs A{};
     A.fx = d_fx; A.fz = d_fz; A.F = F; A.d1 = c->d_d1; A.alpha = c->d_alpha; A.tof = d_tof; A.kmin = d_kmin;
-    A.alpha_out = d_alpha; A.z_el = c->params_d; A.counter = c->d_counter;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
+    A.alpha_out = d_alpha; A.z_el = c->params_d;
+    cudaError_t ce;
+    A.counter = c->take_counter(st, &ce);
+    CUDA_TRY(ce);
     int occ = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_fermat_kernel, kFermatThreads, smem));
     const long long items = ((F + kFermatThreads - 1) / kFermatThreads) * E;
@@ -871,7 +933,7 @@ int tofrt_fermat3d_setup(tofrt_ctx *c, const double *ang, int n_side, const doub
     tofrt_f3d_prepare_kernel<<<grid, 128>>>(S, A, c->f3_smp);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaFuncSetAttribute(tofrt_fermat3d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(ns * sizeof(float4))));
+                                  (int)kMaxDynSmem));
     CUDA_TRY(cudaDeviceSynchronize());
     c->f3_ready = true;
     return TOFRT_OK;
@@ -892,8 +954,10 @@ int tofrt_fermat3d_dev(tofrt_ctx *c, const double *d_fx, const double *d_fy, con
     A.fx = d_fx; A.fy = d_fy; A.fz = d_fz; A.F = F; A.smp = c->f3_smp;
     A.ang = c->f3_geo; A.ex = c->f3_geo + n; A.ey = c->f3_geo + n + E3;
     A.E = E3; A.n_side = n; A.z_el = c->params_d; A.cell = c->f3_cell;
-    A.tof = d_tof; A.kmin = d_kmin; A.ab = d_ab; A.counter = c->d_counter;
-    CUDA_TRY(cudaMemsetAsync(c->d_counter, 0, 5 * sizeof(unsigned long long), st));
+    A.tof = d_tof; A.kmin = d_kmin; A.ab = d_ab;
+    cudaError_t ce;
+    A.counter = c->take_counter(st, &ce);
+    CUDA_TRY(ce);
     int occ = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_fermat3d_kernel, kF3dThreads, smem));
     const long long items = ((F + kF3dThreads - 1) / kF3dThreads) * E3;

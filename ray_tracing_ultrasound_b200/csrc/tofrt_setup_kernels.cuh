@@ -42,3 +42,25 @@ __global__ void tofrt_chord_kernel(int K, const double2 *lens, double2 *seg)
     seg[j] = make_double2(m_seg, b_seg);
 }
 
+
+// per-ray tables in the order the table kernel walks them: lane l of a warp takes the consecutive rays
+// l*C .. l*C + C-1, so plane[c][l] = value of ray min(l*C + c, K-1) makes every load one coalesced line
+__global__ void tofrt_transpose_kernel(DevSetup S, double *ray_t)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long plane = (long long)S.C * 32;
+    if (i >= plane * S.n_shooters) return;
+    const int s = (int)(i / plane), r = (int)(i - (long long)s * plane), c = r >> 5, lane = r & 31;
+    const int k = min(lane * S.C + c, S.K - 1);
+    const size_t o = (size_t)s * S.K + k;
+    double *dst = ray_t + (size_t)s * kRayPlanes * plane + r;
+    const double2 pk = S.lens[k];
+    dst[kPlaneXp * plane] = pk.x;
+    dst[kPlaneZp * plane] = pk.y;
+    dst[kPlaneCpq * plane] = S.cpq[o];
+    dst[kPlaneSpq * plane] = S.spq[o];
+    dst[kPlaneZf * plane] = S.z_f[k];
+    dst[kPlaneApq * plane] = S.a_pq[o];
+    dst[kPlaneBpq * plane] = S.b_pq[o];
+    dst[kPlanePhi * plane] = S.phi_pq[o];
+}

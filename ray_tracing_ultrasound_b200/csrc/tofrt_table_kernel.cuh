@@ -16,27 +16,53 @@ __device__ __noinline__ int scan_exact_from(const double2 *lens, int N, double m
     return -1;
 }
 
-// main_rt.py:106-168: intersect the line with chord (idx, idx+1)
+// test hook (tofrt_debug_search_host): the reflected line of ray [w][k] replaced by a given one.  Out of line so
+// that the production stream carries one uniform branch for it and nothing else.
+__device__ __noinline__ double2 inject_line(const double *inject_m, const double *inject_b, size_t o)
+{
+    return make_double2(inject_m[o], inject_b[o]);
+}
+
+// main_rt.py:106-168: intersect the line with chord (idx, idx+1).
+// PLAIN (uniform, decided per setup on the actual table): no chord is "vertical" in the sense of :110
+// (np.isclose(x1, x2) is false for every j), the abscissae increase and every sample is finite -- the same
+// decisions and the same bits with fewer tests per ray.
+template <bool PLAIN>
 __device__ __forceinline__ void chord_intersection(const double2 *lens, const double2 *seg, int idx, double m,
                                                    double b, double *xi, double *zi)
 {
-    double2 p1 = lens[idx], p2 = lens[idx + 1], sg = seg[idx];
-    double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
+    const double2 p1 = lens[idx], p2 = lens[idx + 1], sg = seg[idx];
+    const double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
+    const double m_seg = sg.x, b_seg = sg.y;  // :127-128
+    if (PLAIN) {
+        // :147-168, the common case
+        const double x_int = (b_seg - b) / (m - m_seg);
+        const double y_int = m * x_int + b;
+        const bool up = y2 > y1;  // finite table entries: one comparison orders them like py_min / py_max
+        const double y_lo = up ? y1 : y2, y_hi = up ? y2 : y1;
+        bool ok = x_int >= x1 - 1e-9 && x_int <= x2 + 1e-9 && y_int >= y_lo - 1e-9 && y_int <= y_hi + 1e-9;
+        double rx = x_int, ry = y_int;
+        if (np_isclose(m, m_seg, 1e-5, 1e-8)) {  // :131-144 parallel (rare: a separate, divergent path)
+            ok = np_isclose(b, b_seg, 1e-5, 1e-8);
+            rx = (x1 + x2) / 2.0;
+            ry = m * rx + b;
+        }
+        *xi = ok ? rx : NAN;
+        *zi = ok ? ry : NAN;
+        return;
+    }
     double rx = NAN, ry = NAN;
     if (np_isclose(x1, x2, 1e-5, 1e-8)) {  // :110-123 vertical chord
         double y_int = m * x1 + b;
         if (y_int >= py_min(y1, y2) - 1e-9 && y_int <= py_max(y1, y2) + 1e-9) { rx = x1; ry = y_int; }
-    } else {
-        double m_seg = sg.x, b_seg = sg.y;  // :127-128
-        if (np_isclose(m, m_seg, 1e-5, 1e-8)) {  // :131-144 parallel
-            if (np_isclose(b, b_seg, 1e-5, 1e-8)) { rx = (x1 + x2) / 2.0; ry = m * rx + b; }
-        } else {  // :147-168
-            double x_int = (b_seg - b) / (m - m_seg);
-            double y_int = m * x_int + b;
-            if (x_int >= py_min(x1, x2) - 1e-9 && x_int <= py_max(x1, x2) + 1e-9 &&
-                y_int >= py_min(y1, y2) - 1e-9 && y_int <= py_max(y1, y2) + 1e-9) {
-                rx = x_int; ry = y_int;
-            }
+    } else if (np_isclose(m, m_seg, 1e-5, 1e-8)) {  // :131-144 parallel
+        if (np_isclose(b, b_seg, 1e-5, 1e-8)) { rx = (x1 + x2) / 2.0; ry = m * rx + b; }
+    } else {  // :147-168
+        double x_int = (b_seg - b) / (m - m_seg);
+        double y_int = m * x_int + b;
+        if (x_int >= py_min(x1, x2) - 1e-9 && x_int <= py_max(x1, x2) + 1e-9 &&
+            y_int >= py_min(y1, y2) - 1e-9 && y_int <= py_max(y1, y2) + 1e-9) {
+            rx = x_int; ry = y_int;
         }
     }
     *xi = rx; *zi = ry;
@@ -46,8 +72,16 @@ __device__ __forceinline__ void chord_intersection(const double2 *lens, const do
 // HG: first-hit state in the output rows (global memory) instead of warp-private shared memory
 // GUIDED: compile the guided search (its rare fallback is then a plain per-ray exact scan) or the
 // warp-wide literal scan -- two lean instruction streams instead of one kernel carrying both.
-// VEC: the two return-path interface laws in vector form (tofrt_raymath.h) instead of the reference's angles
-template <bool HG, bool GUIDED, bool FLAT, bool VEC>
+// VEC: the return-path arithmetic in vector form (tofrt_raymath.h) instead of the reference's angles
+// STATS: count the executed work (rays per stage, probes, exact diffs) into T.stats -- an instrumented twin of
+// the production instantiation, used by bench.py outside the timed region (roofline.executed)
+//
+// Ray order.  A warp owns one (shooter, geometry); lane l walks the CONSECUTIVE rays l*C .. l*C + C-1
+// (C = ceil(K / 32); indices beyond K-1 repeat ray K-1, which is idempotent: same landing point, same
+// atomicMin).  Consecutive rays enter the lens at neighbouring samples, so the bracket of the previous ray
+// predicts the next one to +-1 sample (section 4c of docs/guided_search.md).  The per-ray tables are stored
+// transposed ([plane][c][lane], tofrt_transpose_kernel) so that each load stays one coalesced line.
+template <bool HG, bool GUIDED, bool FLAT, bool VEC, bool STATS>
 __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_BLOCKS)
     tofrt_table_kernel(DevSetup S, TableArgs T)
 {
@@ -62,7 +96,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
     double *s_tof = s_xs + S.E_sorted;               // [kWarps][E] (absent when HG)
     int *s_perm = reinterpret_cast<int *>(s_tof + (HG ? (size_t)0 : (size_t)kWarps * E));
     int *s_khit = s_perm + S.E_sorted;               // [kWarps][E] (absent when HG)
-    int *s_bucket = s_khit + (HG ? (size_t)0 : (size_t)kWarps * E);  // [nb]
+    int *s_bucket = s_khit + (HG ? (size_t)0 : (size_t)kWarps * E);  // [nb] packed (first, count)
 
     // Stage the sampled surface once per CTA: two TMA bulk copies (lens samples, chords; 16-byte
     // aligned, multiples of 16 bytes) complete on one mbarrier while the threads load the small
@@ -89,10 +123,18 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
     typedef typename std::conditional<HG, volatile int, int>::type khit_t;
     tof_t *w_tof = s_tof + (size_t)warp * E;
     khit_t *w_khit = s_khit + (size_t)warp * E;
-    const int nchunks = (K + 31) >> 5;
+    const int C = S.C;               // rays per lane
+    const int k_first = lane * C;    // this lane's first ray
+    const size_t plane = (size_t)C * 32;
     const unsigned FULL = 0xffffffffu;
-    const double cand_lo = S.rx_min - S.tol_max, cand_hi = S.rx_max + S.tol_max;  // aperture +- largest tolerance
-    unsigned st_rays = 0, st_scan_rays = 0, st_scan_warps = 0, st_onsample = 0;
+    tofrt_vec_lens VL = S.VL;  // lens constants of the vector form (uniform)
+    VL.flat = FLAT ? 1 : 0;
+    // executed-work counters (STATS only): rays, rays with a bracket, cond probes, exact diffs, rays that entered
+    // the lens again, rays that reached the landing point, receiver candidates tested, winners (legs computed),
+    // rays in a fallback bisection, rays in the exact O(N) scan, on-sample passes
+    unsigned st[kNumStats];
+#pragma unroll
+    for (int i = 0; i < kNumStats; ++i) st[i] = 0;
 
     // Work distribution: the CTA takes kWarps consecutive (shooter, geometry) items at a time, one per
     // warp, and its warps start them together (two block barriers per ~40 us of work).  Warps that
@@ -111,27 +153,35 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
         const long long w = (long long)g64;               // work item = (shooter, geometry)
         long long g = w, s_local = 0;
         if (T.s_count > 1) { s_local = w / T.G; g = w - s_local * T.G; }  // 64-bit division only when several shooters
-        const size_t sk = (size_t)(T.s_begin + s_local) * K;  // offset of the shooter's per-ray tables
+        const int shooter = T.s_begin + (int)s_local;
+        const double *ray_t = S.ray_t + (size_t)shooter * kRayPlanes * plane + lane;  // [plane][c][lane]
         const double r_outer = T.radius[g], pipe_offset = T.offset[g];
-        const double rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset;
+        const double rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset, rsq2 = rsq * rsq;
         if (HG) { w_tof = T.tof + (size_t)w * E; w_khit = T.k_hit + (size_t)w * E; }
         for (int e = lane; e < E; e += 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0; }
         __syncwarp();
 
-        int h1 = -1, h2 = -1;  // guided search: this lane's bracket starts in the previous two chunks
-        for (int c = 0; c < nchunks; ++c) {
-            const int k = (c << 5) + lane;
-            const bool valid = k < K;
-            const int kk = valid ? k : K - 1;
+        int h1 = -1, h2 = -1;  // guided search: this lane's bracket starts for the previous two rays
+        for (int c = 0; c < C; ++c) {
+            const int k = min(k_first + c, K - 1);
             // per-ray constants of the shot: one coalesced, L1-resident load per 32 rays
-            const double a_pq = __ldg(S.a_pq + sk + kk), b_pq = __ldg(S.b_pq + sk + kk);
-            const double phi_pq = VEC ? 0.0 : __ldg(S.phi_pq + sk + kk);
-            const double cpq = VEC ? __ldg(S.cpq + sk + kk) : 0.0, spq = VEC ? __ldg(S.spq + sk + kk) : 0.0;
-            const double z_f = __ldg(S.z_f + kk);
+            const double *rt = ray_t + (size_t)c * 32;
+            const double z_f = __ldg(rt + kPlaneZf * plane);
 
-            // ---- main_rt.py:351-364 pipe intersection, upper root ----
             double x_q, z_q;
-            {
+            double phi_l = 0.0, cl = 0.0, sl = 0.0, m, b;  // reflected direction: angle, or r^2 (cos, sin)
+            if (VEC) {
+                const double xp = __ldg(rt + kPlaneXp * plane), zp = __ldg(rt + kPlaneZp * plane);
+                const double cpq = __ldg(rt + kPlaneCpq * plane), spq = __ldg(rt + kPlaneSpq * plane);
+                // ---- main_rt.py:351-364 pipe intersection, upper root; :367-376 reflection on the pipe ----
+                tofrt_vec_pipe(xp, zp, cpq, spq, pipe_offset, rsq, &x_q, &z_q);
+                tofrt_vec_reflect(x_q, rsq, cpq, spq, &cl, &sl);
+                m = sl / cl;
+                b = fma(-m, x_q, z_q);
+            } else {
+                const double a_pq = __ldg(rt + kPlaneApq * plane), b_pq = __ldg(rt + kPlaneBpq * plane);
+                const double phi_pq = __ldg(rt + kPlanePhi * plane);
+                // ---- main_rt.py:351-364 pipe intersection, upper root ----
                 double A2 = a_pq * a_pq + 1;
                 double B2 = 2 * (a_pq * b_pq - pipe_offset);
                 double C2 = offsq + b_pq * b_pq - rsq;
@@ -142,14 +192,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 bool up = z_q1 > z_q2;
                 x_q = up ? x_q1 : x_q2;
                 z_q = up ? z_q1 : z_q2;
-            }
-            // ---- main_rt.py:367-376 reflection on the pipe ----
-            double phi_l = 0.0, cl = 0.0, sl = 0.0, m, b;  // reflected direction: angle, or r^2 (cos, sin)
-            if (VEC) {
-                tofrt_vec_reflect(x_q, rsq, cpq, spq, &cl, &sl);
-                m = sl / cl;
-                b = z_q - m * x_q;
-            } else {
+                // ---- main_rt.py:367-376 reflection on the pipe ----
                 double slope = -x_q / sqrt(rsq - x_q * x_q);  // dzdx_pipe ignores the offset (:237-238)
                 double phi_slope = tofrt_atan(slope);
                 double theta_1 = phi_pq - (phi_slope + HALF_PI);
@@ -157,42 +200,41 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 m = tofrt_tan(phi_l);
                 b = z_q - m * x_q;
             }
-            if (T.inject_m) {  // test hook: search an arbitrary line instead (uniform branch, off in production)
-                m = T.inject_m[(size_t)w * K + kk];
-                b = T.inject_b[(size_t)w * K + kk];
-            }
+            if (T.inject_m) { const double2 mb = inject_line(T.inject_m, T.inject_b, (size_t)w * K + k); m = mb.x; b = mb.y; }  // test hook, off in production
 
             // ---- main_rt.py:78-99 first sign change over the sampled lens ----
             // fast path precondition: every diff is finite, so only {-,0,+} occur
-            const bool fast = valid && S.tables_ok && fabs(m) < 1e150 && fabs(b) < 1e150;
+            const bool fast = S.tables_ok && fabs(m) < 1e150 && fabs(b) < 1e150;
             int idx = -1;             // >= 0 segment, -1 none
             bool need_scan = fast;    // lanes whose index the O(N) scan below still has to find
             bool skip_on_sample = false;
             if (GUIDED) {
-                // ---- guided search: same idx as the scan, in O(log N) diffs ------------------
+                // ---- guided search: same idx as the scan, in O(1) diffs (docs/guided_search.md) --------
                 // g_j = shape * diff_j is, in exact arithmetic, a concave sequence over the sampled
                 // lens (chord slopes strictly monotone, checked by tofrt_setup), and a computed diff
                 // differs from the exact one by < tol = 2^-48 (|m| X + |b| + Z).  So a diff beyond
                 // +-tol has a certain sign, a concave sequence is >= the smaller of two of its values
                 // in between, and it is monotone on either side of its maximum: that brackets the
-                // first sign change to [lo, lo+1] with every earlier sign known; the exact scan then
+                // first sign change to [lo, lo+1] with every earlier sign known; the exact test then
                 // starts at lo.  Anything uncertain (|diff| <= tol where it matters) falls back to the
                 // full scan, so the result is identical by construction.
                 const double sh = (double)S.shape;
                 const double tol = (fabs(m) * S.X + fabs(b) + S.Z) * 0x1p-48 + 1e-290;
-                const double g0 = sh * line_diff(s_lens[0], m, b);
-                const double gN = sh * line_diff(s_lens[N - 1], m, b);
+                const double d0 = line_diff(S.P0, m, b);   // first and last lens sample: setup constants
+                const double g0 = sh * d0;
+                const double gN = sh * line_diff(S.PN, m, b);
                 const bool pos0 = g0 > tol, neg0 = g0 < -tol;
                 bool bracket = false, certain_none = false;
                 double edge = 0.0;  // lower bound of min|diff| when there is certainly no change
                 if (fast && pos0 && gN > tol) { certain_none = true; edge = fmin(g0, gN) - tol; }
                 else if (fast && (pos0 || neg0)) bracket = true;
-                // One bisection serves both cases.  lo advances to mid iff g_mid certainly has the
-                // sign of g_0 and, when g_0 < 0, mid is still before the maximum of g (chord slope
-                // on the rising side): then every sample up to mid certainly has that sign too.
+                // cond(j): sample j certainly has the sign of g_0 and, when g_0 < 0, lies on the rising side
+                // (chord slope above m): then every sample up to j certainly has that sign too.  ANY j
+                // with cond(j) is a valid lower end of the bracket, any j without it a valid upper end
+                // (the concavity arguments do not depend on how j was chosen, docs/guided_search.md).
                 const double sgn = pos0 ? sh : -sh;
                 const double ms_eff = pos0 ? -INFINITY : sh * m;
-                // "diff_mid certainly has the sign of diff_0", one fused operation per probe:
+                // "diff_j certainly has the sign of diff_0", one fused operation per probe:
                 //   sgn (z - m x - b) > tol   <=   sgn z > fma(sgn m, x, sgn b + tol)
                 // (sgn = +-1: the products are exact; the two roundings are < tol/16, see docs/guided_search.md)
                 const double cm = sgn * m, cbt = sgn * b + tol;
@@ -200,43 +242,52 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 const int sflip = S.shape < 0 ? (int)0x80000000 : 0;  // uniform: sh * slope by a sign flip
                 const char *lens_b = reinterpret_cast<const char *>(s_lens);
                 const int slope_off = (int)(reinterpret_cast<const char *>(s_seg) - lens_b);  // uniform
-                // cond(j): sample j certainly has the sign of g_0 and (g_0 < 0) lies on the rising side.  ANY j
-                // with cond(j) is a valid lower end of the bracket, any j without it a valid upper end
-                // (the concavity arguments do not depend on how j was chosen, docs/guided_search.md).
                 auto cond_at = [&](int j) {
                     const char *pa = lens_b + j * 16;  // lens[j]; the chord slope sits slope_off bytes further
                     const double2 pm = *reinterpret_cast<const double2 *>(pa);
                     const double slope = *reinterpret_cast<const double *>(pa + slope_off);
                     const double zs = __hiloint2double(__double2hiint(pm.y) ^ zflip, __double2loint(pm.y));
                     const double ss = __hiloint2double(__double2hiint(slope) ^ sflip, __double2loint(slope));
+                    if (STATS) st[kStProbes] += bracket;
                     return (zs > fma(cm, pm.x, cbt)) && (ss > ms_eff);
                 };
-                int lo = 0, hi = N - 1, nsteps = S.log2n;
-                // Predicted bracket: along a shot the entry index is a smooth function of the ray index, so
-                // this lane's brackets of the previous two chunks extrapolate to within a few samples
-                // (measured on config 3: +-4 covers 96 % of the chunks, +-8 99.6 %).  Two probes certify [p - W, p + W] as a
-                // bracket for every lane of the warp, and the bisection needs log2(2 W) steps instead of
-                // log2(N); otherwise the full bisection runs as before.
-#ifndef TOFRT_PRED_W  /* measured: W = 4 (3 steps) 7.81 ms, W = 8 (4 steps) 7.91 ms, W = 16 (5 steps) 8.11 ms; none: 8.44 ms */
-#define TOFRT_PRED_W 4
-#define TOFRT_PRED_STEPS 3
-#endif
-                constexpr int kPredW = TOFRT_PRED_W, kPredSteps = TOFRT_PRED_STEPS;  // 2 * kPredW <= 2^kPredSteps
-                if (__all_sync(FULL, !bracket || (h1 >= 0 && h2 >= 0))) {
-                    const int p = 2 * h1 - h2;
-                    const int plo = min(max(p - kPredW, 0), N - 2), phi = min(plo + 2 * kPredW, N - 1);
-                    const bool okp = cond_at(plo) && !cond_at(phi);
-                    if (__all_sync(FULL, !bracket || okp)) { lo = plo; hi = phi; nsteps = kPredSteps; }
+                int lo = 0, hi = N - 1;
+                // Window around the prediction: lane-local extrapolation of the previous two rays' bracket
+                // starts (one when only one is known).  Four probes at p-1 .. p+2 find a pair
+                // cond(L) && !cond(L+1) for 96 % of the rays; the others run the bisection below, narrowed by
+                // what the window already certified.
+                const int p = h1 >= 0 ? (h2 >= 0 ? 2 * h1 - h2 : h1) : -1;
+                bool open = bracket;  // lanes whose bracket is still wider than one chord
+                if (__any_sync(FULL, bracket && p >= 0)) {
+                    // cond is only ever evaluated at samples <= N-2 (the last sample has no chord); a clamped
+                    // duplicate repeats its neighbour's value, so its pair can never fire
+                    const int w0 = min(max(p - 1, 0), N - 2);
+                    const int w1 = min(w0 + 1, N - 2), w2 = min(w0 + 2, N - 2), w3 = min(w0 + 3, N - 2);
+                    const bool c0 = cond_at(w0), c1 = cond_at(w1), c2 = cond_at(w2), c3 = cond_at(w3);
+                    if (p >= 0) {
+                        if (c0 && !c1) { lo = w0; hi = w1; }
+                        else if (c1 && !c2) { lo = w1; hi = w2; }
+                        else if (c2 && !c3) { lo = w2; hi = w3; }
+                        else if (c3) lo = w3;       // the whole window certainly keeps the sign: search to its right
+                        // no pair and c3 false => c0 false (else c1, c2, c3 would follow): w0 is a valid upper end;
+                        // at w0 = 0 the same argument makes c1 false, and sample 1 takes its place (lo = 0 needs no test)
+                        else hi = w0 > 0 ? w0 : 1;
+                    }
+                    open = bracket && (hi - lo > 1);
                 }
-                for (int it = 0; it < nsteps; ++it) {
-                    const int mid = (lo + hi) >> 1;  // <= N-2 whenever hi - lo > 1
-                    const bool cond = cond_at(mid);
-                    const bool act = bracket && (hi - lo > 1);
-                    lo = (act && cond) ? mid : lo;
-                    hi = (act && !cond) ? mid : hi;
+                if (__any_sync(FULL, open)) {  // bisection for the lanes the window did not settle (others idle)
+                    if (STATS) st[kStFallback] += open;
+                    for (int it = 0; it < S.log2n; ++it) {
+                        const int mid = (lo + hi) >> 1;  // <= N-2 whenever hi - lo > 1
+                        const bool cond = cond_at(mid);
+                        const bool act = bracket && (hi - lo > 1);
+                        lo = (act && cond) ? mid : lo;
+                        hi = (act && !cond) ? mid : hi;
+                        if (!__any_sync(FULL, bracket && (hi - lo > 1))) break;
+                    }
                 }
-                h2 = h1;
-                h1 = bracket ? lo : -1;
+                if (bracket) { h2 = h1; h1 = lo; } else h2 = -1;  // history: keep the last bracket across rays without one
+                if (STATS) st[kStBracket] += bracket;
                 if (bracket && hi - lo > 1) { bracket = false; }  // cannot happen (log2n steps suffice); scan if it did
                 if (bracket && neg0) {
                     // hi = lo + 1 failed the test (or is the untested last sample).  If g_hi is still
@@ -246,21 +297,22 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                     // sample on, the maximum is g_0 -- so the bound below uses the larger of the two)
                     // ("certainly negative" must be the loop's own probe: hi may have failed exactly that)
                     const double2 ph = s_lens[hi];
-                    const double ghi = sh * line_diff(ph, m, b);
-                    const double glo = sh * line_diff(s_lens[lo], m, b);
                     const double zh = __hiloint2double(__double2hiint(ph.y) ^ zflip, __double2loint(ph.y));
-                    if (zh > fma(cm, ph.x, cbt)) { bracket = false; certain_none = true; edge = -fmax(ghi, glo) - tol; }
+                    if (zh > fma(cm, ph.x, cbt)) {
+                        const double ghi = sh * line_diff(ph, m, b);
+                        const double glo = sh * line_diff(s_lens[lo], m, b);
+                        bracket = false; certain_none = true; edge = -fmax(ghi, glo) - tol;
+                    }
                 }
                 if (bracket) {
-                    // exact classes from lo on (normally one step)
-                    int cprev = sign_class(line_diff(s_lens[lo], m, b));
-                    int j = lo;
-                    for (; j + 1 < N; ++j) {
-                        int cnext = sign_class(line_diff(s_lens[j + 1], m, b));
-                        if (class_change(cprev, cnext)) break;
-                        cprev = cnext;
-                    }
-                    if (j + 1 < N) idx = j;
+                    // Every sample up to lo has a non-zero computed diff with the sign of diff_0 (the invariant),
+                    // so the first change is at lo iff diff_{lo+1} does not strictly share that sign (zero, the
+                    // other sign or NaN: np.sign differs); otherwise keep going exactly (rare).
+                    const double dn = line_diff(s_lens[lo + 1], m, b);
+                    if (STATS) st[kStDiffs] += 1;
+                    const bool same = d0 > 0.0 ? dn > 0.0 : dn < 0.0;
+                    if (!same) idx = lo;
+                    else if (lo + 2 < N) idx = scan_exact_from(s_lens, N, m, b, lo + 1);
                     need_scan = false;  // no change after lo either => none at all (on-sample test decides)
                 } else if (certain_none) {
                     need_scan = false;
@@ -269,13 +321,11 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
             }
             int flagged = -1;
             unsigned gmin = 0xffffffffu;  // min over all chunks of the high words (see below)
-            st_rays += valid; st_scan_rays += need_scan;
+            if (STATS) { st[kStRays] += 1; st[kStScan] += need_scan; }
             if (GUIDED) {
                 // a ray the guided search could not decide (|diff| <= tol where it matters): plain exact scan
-                if (__any_sync(FULL, need_scan)) st_scan_warps += (lane == 0);
                 if (need_scan) { idx = scan_exact_from(s_lens, N, m, b, 0); flagged = 0; }
             } else if (__any_sync(FULL, need_scan)) {
-                st_scan_warps += (lane == 0);
                 unsigned hp = hi32(line_diff(s_lens[0], m, b));
                 for (int base = 1; base < Npad; base += kChunk) {
                     unsigned mn = hp, mx = hp;
@@ -287,6 +337,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                         mx = __vimax3_u32(mx, ha, hb);
                         hp = hb;
                     }
+                    if (STATS) st[kStDiffs] += kChunk;
                     gmin = min(gmin, mn);
                     // sign differs inside the chunk, or a +-0 (high word 0 / 0x80000000) occurred
                     bool flag = ((int)(mn ^ mx) < 0) || ((mn << 1) == 0u);
@@ -311,8 +362,12 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 }
                 if (chg) idx = j0 + __ffs(chg) - 1;  // padding repeats the last sample: never a change there
             }
-            if (valid && idx < 0) {
-                if (!fast) idx = scan_exact_from(s_lens, N, m, b, 0);
+            if (idx < 0) {
+                if (!fast) {
+                    // a NaN line makes every diff NaN: np.sign changes "between" samples 0 and 1 (main_rt.py:82)
+                    if (m != m || b != b) idx = 0;
+                    else idx = scan_exact_from(s_lens, N, m, b, 0);
+                }
                 // conservative flag without a real change (a denormal diff): keep going exactly
                 else if (!GUIDED && need_scan && flagged >= 0 && flagged + kChunk - 1 < N - 1)
                     idx = scan_exact_from(s_lens, N, m, b, flagged + kChunk - 1);
@@ -323,11 +378,11 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
             // need the test.  It is warp-cooperative: 32 lanes take 32 consecutive samples of one ray.
             int on_sample = -1;
             {
-                bool maybe = valid && idx < 0 && !skip_on_sample &&
+                bool maybe = idx < 0 && !skip_on_sample &&
                              (!fast || !need_scan || flagged >= 0 ||
                               (gmin & 0x7fffffffu) <= 0x3e45798eu /* hi32(1e-8) */);
                 unsigned need = __ballot_sync(FULL, maybe);
-                st_onsample += (lane == 0) ? __popc(need) : 0;
+                if (STATS) st[kStOnSample] += maybe;
                 while (need) {
                     int src = __ffs(need) - 1;
                     need &= need - 1;
@@ -342,42 +397,46 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 }
             }
             double ix = NAN, iz = NAN;
-            if (idx >= 0) chord_intersection(s_lens, s_seg, idx, m, b, &ix, &iz);
+            if (idx >= 0) {
+                if (S.chords_plain) chord_intersection<true>(s_lens, s_seg, idx, m, b, &ix, &iz);
+                else chord_intersection<false>(s_lens, s_seg, idx, m, b, &ix, &iz);
+            }
             else if (on_sample >= 0) { double2 s = s_lens[on_sample]; ix = s.x; iz = s.y; }
 
             // ---- main_rt.py:396-405 refraction back into the lens, landing point ----
             // NaN in -> NaN out, so whole 32-ray groups that missed the lens, or are totally
             // reflected (|sin| > 1 in main_rt.py:277), skip the rest of the arithmetic.
             double target_x = NAN;
-            if (__any_sync(FULL, valid && ix == ix)) {
+            if (STATS) st[kStLens2] += ix == ix;
+            if (VEC) {
+                if (__any_sync(FULL, ix == ix)) {
+                    double tz, tx, nn, w2;
+                    tofrt_vec_return_head(&VL, ix, iz, cl, sl, rsq2, &tz, &tx, &nn, &w2);
+                    if (STATS) st[kStLanding] += w2 >= 0.0;
+                    if (__any_sync(FULL, w2 >= 0.0)) target_x = tofrt_vec_return_tail(ix, iz, z_f, tz, tx, nn, w2);
+                }
+            } else if (__any_sync(FULL, ix == ix)) {
                 // alpha_i = arctan2(ix, iz) is only ever used through sin/cos (main_rt.py:396-397):
                 // one fused elementary function, no angle
                 double sn, cs, h, dz, dx;
                 tofrt_sincos_atan2(ix, iz, &sn, &cs);
                 lens_point_t<FLAT>(S, sn, cs, &h, &dz, &dx);
                 // refraction(phi_l, (dz, dx), c2, c1), main_rt.py:272-278
-                double phi_slope = 0.0, s_arg;
-                if (VEC) s_arg = S.c1_over_c2 * tofrt_vec_sin_theta1(cl, sl, rsq, dz, dx);
-                else {
-                    phi_slope = tofrt_atan2(dz, dx);
-                    double theta_1 = phi_l - (phi_slope + HALF_PI);
-                    s_arg = S.c1_over_c2 * tofrt_sin(theta_1);
-                }
-                if (__any_sync(FULL, valid && fabs(s_arg) <= 1.0)) {
-                    double a_i;
-                    if (VEC) a_i = tofrt_vec_refract_slope(s_arg, dz, dx);
-                    else {
-                        double theta_2 = tofrt_asin(s_arg);
-                        double phi_last = phi_slope - HALF_PI + theta_2;
-                        a_i = tofrt_tan(phi_last);
-                    }
+                double phi_slope = tofrt_atan2(dz, dx);
+                double theta_1 = phi_l - (phi_slope + HALF_PI);
+                double s_arg = S.c1_over_c2 * tofrt_sin(theta_1);
+                if (STATS) st[kStLanding] += fabs(s_arg) <= 1.0;
+                if (__any_sync(FULL, fabs(s_arg) <= 1.0)) {
+                    double theta_2 = tofrt_asin(s_arg);
+                    double phi_last = phi_slope - HALF_PI + theta_2;
+                    double a_i = tofrt_tan(phi_last);
                     double b_i = iz - a_i * ix;
                     target_x = (z_f - b_i) / a_i;
                 }
             }
 
             // ---- optional per-ray records ----
-            if (T.any_rec && valid) {  // one uniform test in table-only mode
+            if (T.any_rec) {  // one uniform test in table-only mode
                 size_t o = (size_t)w * K + k;
                 if (T.rec.pipe_x) T.rec.pipe_x[o] = x_q;
                 if (T.rec.pipe_z) T.rec.pipe_z[o] = z_q;
@@ -388,45 +447,45 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
             }
 
             // ---- main_rt.py:487-501 which receivers does this ray land on? ----
-            // candidates: finite receivers within tol_max of target_x (binary search in the
-            // sorted copy); the exact np.isclose decides.  +-inf landing points can only match
-            // an identical infinite receiver.
-            bool cand = valid && target_x >= cand_lo && target_x <= cand_hi;
-            bool special = valid && S.has_nonfinite_rx && isinf(target_x);
+            // Candidates: finite receivers within tol_max of target_x, from a cell table over the aperture
+            // (cell c lists every receiver that any landing point whose computed cell index is c could match:
+            // most cells list none, so most rays leave after one lookup); the exact np.isclose decides.
+            // +-inf landing points can only match an identical infinite receiver.
+            int lo = 0, hi = 0;
+            if (S.nb > 0) {
+                const double cpos = (target_x - S.bx0) * S.binv;
+                // NaN -> cell 0; out-of-range landing points -> the (empty) guard cells at either end
+                const int cell = cpos > 0.0 ? (cpos < (double)(S.nb - 1) ? (int)cpos : S.nb - 1) : 0;
+                const int packed = s_bucket[cell];
+                lo = packed & 0xffff;
+                hi = lo + (int)((unsigned)packed >> 16);
+            } else if (target_x >= S.rx_min - S.tol_max && target_x <= S.rx_max + S.tol_max) {
+                // no cell table (few receivers, or a tolerance as wide as the aperture): binary search
+                const double tl = target_x - S.tol_max, th = target_x + S.tol_max;
+                int r = S.E_sorted;
+                while (lo < r) { int mid = (lo + r) >> 1; if (s_xs[mid] < tl) lo = mid + 1; else r = mid; }
+                hi = lo;
+                while (hi < S.E_sorted && s_xs[hi] <= th) ++hi;
+            }
+            const bool special = S.has_nonfinite_rx && isinf(target_x);
             const bool want_legs = T.rec.legs != nullptr;
-            if (__any_sync(FULL, cand || special || want_legs)) {
-                int lo = 0, hi = 0;
+            if (__any_sync(FULL, hi > lo || special || want_legs)) {
                 bool mine = false;
-                if (cand) {
-                    double tl = target_x - S.tol_max, th = target_x + S.tol_max;
-                    // first sorted receiver >= tl: a bucket lookup (start provably at or before it)
-                    // plus a short forward walk; binary search when no bucket table was built
-                    int l = 0;
-                    if (S.nb > 0) {
-                        const double cpos = (tl - S.bx0) * S.binv;
-                        const int c = cpos > 0.0 ? (cpos < (double)(S.nb - 1) ? (int)cpos : S.nb - 1) : 0;
-                        l = s_bucket[c];
-                        while (l < S.E_sorted && s_xs[l] < tl) ++l;
-                    } else {
-                        int r = S.E_sorted;
-                        while (l < r) { int mid = (l + r) >> 1; if (s_xs[mid] < tl) l = mid + 1; else r = mid; }
-                    }
-                    lo = l;
-                    hi = l;
-                    while (hi < S.E_sorted && s_xs[hi] <= th) ++hi;
-                    for (int i = lo; i < hi; ++i)
-                        if (np_isclose(target_x, s_xs[i], S.rtol, S.atol)) { atomicMin(const_cast<int *>(&w_khit[s_perm[i]]), k); mine = true; }
+                for (int i = lo; i < hi; ++i) {
+                    if (STATS) st[kStCand] += 1;
+                    if (np_isclose(target_x, s_xs[i], S.rtol, S.atol)) { atomicMin(const_cast<int *>(&w_khit[s_perm[i]]), k); mine = true; }
                 }
                 if (special) {
                     for (int e = 0; e < E; ++e)
                         if (target_x == S.x_rx[e]) { atomicMin(const_cast<int *>(&w_khit[e]), k); mine = true; }
                 }
                 __syncwarp();
-                if (mine || (want_legs && valid)) {
+                if (mine || want_legs) {
                     // main_rt.py:497-500 / main_compare.py:514-517
-                    double2 p = s_lens[kk];
-                    double t1 = S.leg1[sk + kk];
-                    double t2 = dist2d(p.x, p.y, x_q, z_q) / S.c2;
+                    if (STATS) st[kStWinners] += 1;
+                    const double2 pk = s_lens[k];
+                    double t1 = S.leg1[(size_t)shooter * K + k];
+                    double t2 = dist2d(pk.x, pk.y, x_q, z_q) / S.c2;
                     double t3 = dist2d(x_q, z_q, ix, iz) / S.c2;
                     double t4 = dist2d(ix, iz, target_x, z_f) / S.c1;
                     if (want_legs) {
@@ -460,11 +519,11 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
         }
         __syncwarp();
     }
-    if (T.stats) {
-        st_rays = __reduce_add_sync(FULL, st_rays); st_scan_rays = __reduce_add_sync(FULL, st_scan_rays);
-        if (lane == 0) {
-            atomicAdd(T.stats + 0, (unsigned long long)st_rays); atomicAdd(T.stats + 1, (unsigned long long)st_scan_rays);
-            atomicAdd(T.stats + 2, (unsigned long long)st_scan_warps); atomicAdd(T.stats + 3, (unsigned long long)st_onsample);
+    if (STATS && T.stats) {
+#pragma unroll
+        for (int i = 0; i < kNumStats; ++i) {
+            unsigned v = __reduce_add_sync(FULL, st[i]);
+            if (lane == 0) atomicAdd(T.stats + i, (unsigned long long)v);
         }
     }
 }

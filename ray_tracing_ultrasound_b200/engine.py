@@ -123,11 +123,20 @@ class TofEngine:
         """+1 concave, -1 convex, 0 neither (guided search falls back to the scan)."""
         return self._lib.tofrt_get_info(self._ctx, 1)
 
+    STAT_KEYS = ("rays", "bracket_rays", "probes", "exact_diffs", "lens2_rays", "landing_rays", "receiver_tests",
+                 "winner_rays", "fallback_rays", "scan_rays", "on_sample_rays")
+
+    def set_stats(self, on):
+        """Run the instrumented instantiation of the table kernel (same results, a little slower) so that
+        last_stats() can report the executed work; see TOFRT_OPT_STATS."""
+        _capi.check(self._lib.tofrt_set_option(self._ctx, 4, 1 if on else 0))
+        return self
+
     def last_stats(self):
-        """Search statistics of the last table call (see tofrt_last_stats)."""
-        arr = (ctypes.c_ulonglong * 4)()
-        _capi.check(self._lib.tofrt_last_stats(self._ctx, arr))
-        return dict(zip(("rays", "scan_rays", "scan_groups", "on_sample_rays"), (int(x) for x in arr)))
+        """Executed-work counters of the last table call made with set_stats(True) (see tofrt_last_stats)."""
+        arr = (ctypes.c_ulonglong * len(self.STAT_KEYS))()
+        _capi.check(self._lib.tofrt_last_stats(self._ctx, arr, len(self.STAT_KEYS)))
+        return dict(zip(self.STAT_KEYS, (int(x) for x in arr)))
 
     def debug_search(self, m, b, with_points=False):
         """Test hook: find_line_curve_intersection of the current setup (current search mode) applied

@@ -21,6 +21,8 @@ Outputs (all np.savez_compressed):
   rays.npz         full per-ray arrays of `shoot_rays` for a geometry subset
   compare_live.npz live reference for the main_compare.py case (K=N=1810)
   shooters.npz     off-centre shooters (parity "unpinned by fixture", live only)
+  array128.npz     live reference with a 128-element array (E = 129: BASELINE configs 3/4) over 96 geometries
+                   of the 1024 x 1024 synthetic grid (`python make_golden.py array128` regenerates only this one)
 """
 import csv
 import importlib.util
@@ -59,7 +61,7 @@ def array_and_alpha(ref, n_alpha):
     x_a = np.arange(ref.num_elements, dtype=np.float64) * ref.pitch
     x_a = x_a - np.mean(x_a)
     x_aux = list(x_a)
-    x_aux.insert(32, np.float64(0.0))
+    x_aux.insert(int(ref.num_elements) // 2, np.float64(0.0))   # 32 in the reference (main_rt.py:472)
     x_a = np.asarray(x_aux, dtype=np.float64)
     z_a = np.ones_like(x_a) * ref.d
     zf = np.ones((ref.num_alpha_points,), dtype=np.float64) * ref.d
@@ -165,9 +167,40 @@ def parse_fixture_csvs():
 RAY_KEYS = ["pipe_x", "pipe_z", "lens_2_x", "lens_2_z", "target_x"]
 
 
+def array128(ref):
+    """BASELINE configs 3/4: the same script with num_elements = 128 (E = 129, shooter = inserted centre element 64)
+    on 96 geometries of the 1024 x 1024 synthetic grid (radius-major np.linspace grid of SURVEY 8(d), flat indices
+    spread evenly with a stride coprime to 1024 so radii and offsets both vary)."""
+    ref.num_elements = np.int64(128)
+    x_a, z_a, zf, alpha = array_and_alpha(ref, 181 * 5)
+    assert len(x_a) == 129 and x_a[64] == 0.0
+    rr = np.linspace(0.01, 0.10, 1024)
+    oo = np.linspace(-0.01, 0.01, 1024)
+    flat = (np.arange(96, dtype=np.int64) * 10939 + 517) % (1024 * 1024)
+    flat = np.sort(flat)
+    out = {k: [] for k in ("hit", "k_hit", "tof", "idx", "margin", "nan_target")}
+    for g in flat:
+        ref.r_outer, ref.pipe_offset = np.float64(rr[g // 1024]), np.float64(oo[g % 1024])
+        res = ref.shoot_rays(x_a[64], z_a[64], zf, alpha, plot=False)
+        idx, margin, nchg, _, _ = reference_idx(ref, x_a[64], z_a[64], alpha, res)
+        hit, k_hit, tof = assemble_table(ref, x_a, z_a, 64, res, atol=1e-6)
+        out["hit"].append(hit); out["k_hit"].append(k_hit); out["tof"].append(tof)
+        out["idx"].append(idx.astype(np.int16)); out["margin"].append(margin.astype(np.float32))
+        out["nan_target"].append(np.isnan(res["target_x"]))
+        print(f"array128 g={g} hits={hit.sum()}", flush=True)
+    np.savez_compressed(os.path.join(OUT, "array128.npz"), x_a=x_a, alpha=alpha, flat_index=flat,
+                        radius=rr[flat // 1024], offset=oo[flat % 1024],
+                        nan_target=np.packbits(np.array(out.pop("nan_target")), axis=1),
+                        **{k: np.array(v) for k, v in out.items()})
+    ref.num_elements = np.int64(64)
+
+
 def main():
     warnings.simplefilter("ignore")
     ref = load_reference()
+    if sys.argv[1:] == ["array128"]:
+        array128(ref)
+        return
     parse_fixture_csvs()
 
     # ---- the main_rt.py sweep (main_rt.py:464-501), K = N = 905 -------------
@@ -255,6 +288,7 @@ def main():
         print(f"shooter {s} r={rr} off={oo}: hits={hit.sum()}")
     np.savez_compressed(os.path.join(OUT, "shooters.npz"), x_a=x_a, alpha=alpha,
                         **{k: np.array(v) for k, v in out.items()})
+    array128(ref)
 
 
 if __name__ == "__main__":

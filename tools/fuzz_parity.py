@@ -35,7 +35,7 @@ mism = 0; fallback = 0; t0 = time.time()
 for lo in range(0, n2, 1000000):
     n = min(1000000, n2 - lo)
     r = torch.from_numpy(rng.uniform(0.002, 0.15, n)).cuda(); of = torch.from_numpy(rng.uniform(-0.04, 0.04, n)).cuda()
-    eng.set_search("guided"); a = eng.tof_table_cuda(r, of); torch.cuda.synchronize(); fallback += eng.last_stats()["scan_rays"]
+    eng.set_search("guided"); eng.set_stats(True); a = eng.tof_table_cuda(r, of); torch.cuda.synchronize(); fallback += eng.last_stats()["scan_rays"]; eng.set_stats(False)
     eng.set_search("scan"); b = eng.tof_table_cuda(r, of); torch.cuda.synchronize()
     mism += int((a.tof != b.tof).sum()) + int((a.k_hit != b.k_hit).sum())
     del a, b
