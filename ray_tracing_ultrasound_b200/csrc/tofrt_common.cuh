@@ -24,7 +24,7 @@ constexpr int kThreadsGuided = TOFRT_THREADS_GUIDED;
 #endif
 constexpr int kChunk = TOFRT_SCAN_CHUNK;  // lens samples per early-exit check of the literal scan (<= 32)
 constexpr int kNoHit = 0x7fffffff;
-// transposed per-ray tables of the FP64 table kernel: ray_t[shooter][plane][c][lane] holds ray min(lane*C + c, K-1)
+// per-ray tables of the FP64 table kernel as planes: ray_t[shooter][plane][r], r < 32 C, holds ray min(r, K-1)
 enum { kPlaneXp, kPlaneZp, kPlaneCpq, kPlaneSpq, kPlaneZf, kPlaneApq, kPlaneBpq, kPlanePhi, kRayPlanes };
 // executed-work counters of the instrumented (STATS) instantiation, per thread-ray (tofrt_last_stats)
 enum { kStRays, kStBracket, kStProbes, kStDiffs, kStLens2, kStLanding, kStCand, kStWinners, kStFallback, kStScan,
@@ -45,8 +45,8 @@ struct DevSetup {
     double rtol, atol, tol_max;              // np.isclose tolerances, and an upper bound of atol+rtol|x_e|
     double rx_min, rx_max;                   // finite receiver range
     int K, Npad, E, E_sorted, has_nonfinite_rx, tables_ok;
-    int C;                 // rays per lane of the table kernel: ceil(K / 32)
-    const double *ray_t;   // [S][kRayPlanes][C][32] transposed per-ray tables
+    int C;                 // 32-ray chunks per shot: ceil(K / 32)
+    const double *ray_t;   // [S][kRayPlanes][32 C] per-ray tables, padded with copies of the last ray
     double2 P0, PN;        // first and last lens sample (the guided search tests them for every ray)
     int chords_plain;    // 1: abscissae strictly increasing and no chord is np.isclose-vertical (main_rt.py:110): checked per setup
     int hits_in_global;  // 1: E too large for the per-warp shared-memory first-hit state -> keep it in the output rows

@@ -118,7 +118,7 @@ struct tofrt_ctx {
     // device buffers owned by the context
     double *d_alpha = nullptr, *d_zf = nullptr, *d_a = nullptr, *d_b = nullptr, *d_phi = nullptr, *d_leg1 = nullptr;
     double *d_cs = nullptr;   // cos / sin of phi_pq, [2][S*K]
-    double *d_ray_t = nullptr;  // transposed per-ray tables of the table kernel
+    double *d_ray_t = nullptr;  // per-ray tables of the table kernel as coalesced planes
     int opt_stats = 0;          // 1: table calls run the instrumented instantiation (tofrt_last_stats)
     double2 *d_lens = nullptr, *d_seg = nullptr;
     int opt_guided = 1;
@@ -294,10 +294,11 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     S.nb = 0; S.bx0 = 0.0; S.binv = 0.0;
 #ifndef TOFRT_NO_BUCKET  /* tuning knob: binary search instead */
     if (S.E_sorted >= 1 && S.E_sorted <= 0xffff) {
-        const int nb = std::min(16 * S.E_sorted + 4, 8192);
+        // three guard cells at either end: cell 0 reaches up to start(3) + tol_max, just short of the first receiver
+        const int nb = std::min(16 * S.E_sorted + 6, 8192);
         const double lo = xs.front() - S.tol_max, range = (xs.back() + S.tol_max) - lo;
-        const double cell = range > 0.0 ? range / (nb - 4) : 1e-300, binv = 1.0 / cell, x0 = lo - 2 * cell;
-        if (std::isfinite(range) && std::isfinite(binv) && cell > 0.0 && std::isfinite(x0) && nb > 4) {
+        const double cell = range > 0.0 ? range / (nb - 6) : 1e-300, binv = 1.0 / cell, x0 = lo - 3 * cell;
+        if (std::isfinite(range) && std::isfinite(binv) && cell > 0.0 && std::isfinite(x0) && nb > 6) {
             bucket.resize(nb);
             int first = 0, last = 0;
             bool ok = true;
@@ -367,7 +368,7 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     CUDA_TRY(cudaGetLastError());
     tofrt_chord_kernel<<<(K + 127) / 128, 128>>>(K, c->d_lens, c->d_seg);
     CUDA_TRY(cudaGetLastError());
-    tofrt_transpose_kernel<<<(unsigned)(((size_t)S.C * 32 * NS + 127) / 128), 128>>>(S, c->d_ray_t);
+    tofrt_ray_table_kernel<<<(unsigned)(((size_t)S.C * 32 * NS + 127) / 128), 128>>>(S, c->d_ray_t);
     CUDA_TRY(cudaGetLastError());
     int bad = 0;
     CUDA_TRY(cudaMemcpy(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost));

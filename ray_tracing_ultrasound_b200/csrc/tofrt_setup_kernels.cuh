@@ -43,15 +43,16 @@ __global__ void tofrt_chord_kernel(int K, const double2 *lens, double2 *seg)
 }
 
 
-// per-ray tables in the order the table kernel walks them: lane l of a warp takes the consecutive rays
-// l*C .. l*C + C-1, so plane[c][l] = value of ray min(l*C + c, K-1) makes every load one coalesced line
-__global__ void tofrt_transpose_kernel(DevSetup S, double *ray_t)
+// per-ray tables of the table kernel as planes [shooter][plane][32 C], C = ceil(K / 32): entry r holds ray
+// min(r, K-1) (the padding repeats the last ray, which the kernel treats as one more, idempotent, copy of it),
+// so a warp's load of 32 consecutive rays is one coalesced line and needs no bounds logic
+__global__ void tofrt_ray_table_kernel(DevSetup S, double *ray_t)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long plane = (long long)S.C * 32;
     if (i >= plane * S.n_shooters) return;
-    const int s = (int)(i / plane), r = (int)(i - (long long)s * plane), c = r >> 5, lane = r & 31;
-    const int k = min(lane * S.C + c, S.K - 1);
+    const int s = (int)(i / plane), r = (int)(i - (long long)s * plane);
+    const int k = min(r, S.K - 1);
     const size_t o = (size_t)s * S.K + k;
     double *dst = ray_t + (size_t)s * kRayPlanes * plane + r;
     const double2 pk = S.lens[k];

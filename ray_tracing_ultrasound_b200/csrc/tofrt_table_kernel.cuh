@@ -76,11 +76,14 @@ __device__ __forceinline__ void chord_intersection(const double2 *lens, const do
 // STATS: count the executed work (rays per stage, probes, exact diffs) into T.stats -- an instrumented twin of
 // the production instantiation, used by bench.py outside the timed region (roofline.executed)
 //
-// Ray order.  A warp owns one (shooter, geometry); lane l walks the CONSECUTIVE rays l*C .. l*C + C-1
-// (C = ceil(K / 32); indices beyond K-1 repeat ray K-1, which is idempotent: same landing point, same
-// atomicMin).  Consecutive rays enter the lens at neighbouring samples, so the bracket of the previous ray
-// predicts the next one to +-1 sample (section 4c of docs/guided_search.md).  The per-ray tables are stored
-// transposed ([plane][c][lane], tofrt_transpose_kernel) so that each load stays one coalesced line.
+// Ray order.  A warp owns one (shooter, geometry) and walks its K rays 32 at a time, lane l of chunk c taking ray
+// 32 c + l (indices beyond K-1 repeat ray K-1, which is idempotent: same landing point, same atomicMin), so the
+// lanes of a warp hold neighbouring rays: they probe neighbouring lens samples (shared-memory broadcast), die
+// together (rays that miss the lens or are totally reflected come in runs) and take the same branches.  The
+// per-ray tables are stored as planes [plane][32 C] (tofrt_ray_table_kernel): every load is one coalesced line.
+// (Measured and rejected: lane l walking the CONSECUTIVE rays l C .. l C + C-1, which predicts the next bracket to
+// +-1 sample from the lane's own previous ray -- the search gets cheaper, but scattered shared-memory probes, the
+// slow paths of the 4 % dead rays now present in every warp and a 2x slower literal scan cost more: 29.8 vs 25.2 ms.)
 template <bool HG, bool GUIDED, bool FLAT, bool VEC, bool STATS>
 __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_BLOCKS)
     tofrt_table_kernel(DevSetup S, TableArgs T)
@@ -123,8 +126,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
     typedef typename std::conditional<HG, volatile int, int>::type khit_t;
     tof_t *w_tof = s_tof + (size_t)warp * E;
     khit_t *w_khit = s_khit + (size_t)warp * E;
-    const int C = S.C;               // rays per lane
-    const int k_first = lane * C;    // this lane's first ray
+    const int C = S.C;               // 32-ray chunks per shot
     const size_t plane = (size_t)C * 32;
     const unsigned FULL = 0xffffffffu;
     tofrt_vec_lens VL = S.VL;  // lens constants of the vector form (uniform)
@@ -161,9 +163,9 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
         for (int e = lane; e < E; e += 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0; }
         __syncwarp();
 
-        int h1 = -1, h2 = -1;  // guided search: this lane's bracket starts for the previous two rays
+        int h1 = -1, h2 = -1;  // guided search: this lane's bracket starts in the previous two chunks
         for (int c = 0; c < C; ++c) {
-            const int k = min(k_first + c, K - 1);
+            const int k = min((c << 5) + lane, K - 1);
             // per-ray constants of the shot: one coalesced, L1-resident load per 32 rays
             const double *rt = ray_t + (size_t)c * 32;
             const double z_f = __ldg(rt + kPlaneZf * plane);
@@ -252,41 +254,45 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                     return (zs > fma(cm, pm.x, cbt)) && (ss > ms_eff);
                 };
                 int lo = 0, hi = N - 1;
-                // Window around the prediction: lane-local extrapolation of the previous two rays' bracket
-                // starts (one when only one is known).  Four probes at p-1 .. p+2 find a pair
-                // cond(L) && !cond(L+1) for 96 % of the rays; the others run the bisection below, narrowed by
-                // what the window already certified.
-                const int p = h1 >= 0 ? (h2 >= 0 ? 2 * h1 - h2 : h1) : -1;
-                bool open = bracket;  // lanes whose bracket is still wider than one chord
-                if (__any_sync(FULL, bracket && p >= 0)) {
-                    // cond is only ever evaluated at samples <= N-2 (the last sample has no chord); a clamped
-                    // duplicate repeats its neighbour's value, so its pair can never fire
-                    const int w0 = min(max(p - 1, 0), N - 2);
-                    const int w1 = min(w0 + 1, N - 2), w2 = min(w0 + 2, N - 2), w3 = min(w0 + 3, N - 2);
-                    const bool c0 = cond_at(w0), c1 = cond_at(w1), c2 = cond_at(w2), c3 = cond_at(w3);
-                    if (p >= 0) {
-                        if (c0 && !c1) { lo = w0; hi = w1; }
-                        else if (c1 && !c2) { lo = w1; hi = w2; }
-                        else if (c2 && !c3) { lo = w2; hi = w3; }
-                        else if (c3) lo = w3;       // the whole window certainly keeps the sign: search to its right
-                        // no pair and c3 false => c0 false (else c1, c2, c3 would follow): w0 is a valid upper end;
-                        // at w0 = 0 the same argument makes c1 false, and sample 1 takes its place (lo = 0 needs no test)
-                        else hi = w0 > 0 ? w0 : 1;
-                    }
-                    open = bracket && (hi - lo > 1);
+                // Predicted bracket: along a shot the entry index is a smooth function of the ray index, so
+                // this lane's brackets of the previous two chunks extrapolate to within a few samples
+                // (measured on config 3: +-4 covers 96 % of the chunks, +-8 99.6 %).  Two probes certify [p - W, p + W] as a
+                // bracket for every lane of the warp, and three straight-line bisection steps finish it;
+                // otherwise the full bisection runs.
+#ifndef TOFRT_PRED_W  /* measured: W = 4 (3 steps) 7.81 ms, W = 8 (4 steps) 7.91 ms, W = 16 (5 steps) 8.11 ms; none: 8.44 ms */
+#define TOFRT_PRED_W 4
+#define TOFRT_PRED_STEPS 3
+#endif
+                constexpr int kPredW = TOFRT_PRED_W, kPredSteps = TOFRT_PRED_STEPS;  // 2 * kPredW <= 2^kPredSteps
+                bool predicted = false;
+                if (__all_sync(FULL, !bracket || (h1 >= 0 && h2 >= 0))) {
+                    const int p = 2 * h1 - h2;
+                    const int plo = min(max(p - kPredW, 0), N - 2), phi = min(plo + 2 * kPredW, N - 1);
+                    const bool okp = cond_at(plo) && !cond_at(phi);
+                    if (__all_sync(FULL, !bracket || okp)) { lo = plo; hi = phi; predicted = true; }
                 }
-                if (__any_sync(FULL, open)) {  // bisection for the lanes the window did not settle (others idle)
-                    if (STATS) st[kStFallback] += open;
+                if (predicted) {
+                    // hi - lo <= 2^kPredSteps: kPredSteps halvings reach hi - lo = 1 (a step at hi - lo = 1 probes
+                    // mid = lo again, cond(lo) holds, nothing moves)
+#pragma unroll
+                    for (int it = 0; it < kPredSteps; ++it) {
+                        const int mid = (lo + hi) >> 1;
+                        const bool cond = cond_at(mid);
+                        lo = cond ? mid : lo;
+                        hi = cond ? hi : mid;
+                    }
+                } else {
+                    if (STATS) st[kStFallback] += bracket;
                     for (int it = 0; it < S.log2n; ++it) {
                         const int mid = (lo + hi) >> 1;  // <= N-2 whenever hi - lo > 1
                         const bool cond = cond_at(mid);
-                        const bool act = bracket && (hi - lo > 1);
+                        const bool act = hi - lo > 1;
                         lo = (act && cond) ? mid : lo;
                         hi = (act && !cond) ? mid : hi;
-                        if (!__any_sync(FULL, bracket && (hi - lo > 1))) break;
                     }
                 }
-                if (bracket) { h2 = h1; h1 = lo; } else h2 = -1;  // history: keep the last bracket across rays without one
+                h2 = h1;
+                h1 = bracket ? lo : -1;
                 if (STATS) st[kStBracket] += bracket;
                 if (bracket && hi - lo > 1) { bracket = false; }  // cannot happen (log2n steps suffice); scan if it did
                 if (bracket && neg0) {

@@ -21,6 +21,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_array128():
+    """Live reference with a 128-element array (tests/golden/make_golden.py array128)."""
+    return np.load(os.path.join(GOLDEN, "array128.npz"))
+
+
+@pytest.fixture(scope="session")
 def oracle_libm():
     from oracle.oracle import Oracle
     return Oracle(device_math=False)

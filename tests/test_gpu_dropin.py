@@ -56,16 +56,20 @@ def test_shoot_rays_dropin_matches_live_reference(golden, engine):
         assert sorted(res) == ["lens_1_x", "lens_1_z", "lens_2_x", "lens_2_z", "pipe_x", "pipe_z", "target_x", "target_z"]
         assert all(v.dtype == np.float64 and v.shape == (905,) for v in res.values())
         assert res["target_z"] is not zf and np.array_equal(res["target_z"], zf)
-        # A ray that grazes the pipe (|x_q - offset| = r to rounding: the centre ray of the degenerate geometries
-        # r = |offset|) has z_q = sqrt(2 r * 1e-17) ~ 1e-10 with a relative error of order one in EVERY formulation,
-        # the reference's included; everywhere else the points agree to a few ulp.
-        grazing = np.abs(np.abs(rays["pipe_x"][i] - main_rt.pipe_offset) - main_rt.r_outer) < 1e-12 * main_rt.r_outer
-        assert grazing.sum() <= 1
+        # Non-degenerate geometries: every point within a few ulp of the live reference.  In a degenerate geometry
+        # r = |offset| the pipe touches the origin, where every ray of the constant-TOF lens is aimed: all rays hit
+        # the pipe at its edge point, z_q = sqrt(r^2 - (x_q - offset)^2) amplifies the last bit of x_q to ~1e-13 there,
+        # and the centre ray (x_q ~ 1e-17) has z_q ~ 1e-10 with a relative error of order one in EVERY formulation --
+        # the reference's own z_q = a_pq x_q + b_pq cancels 16 digits there.
+        degenerate = abs(abs(float(main_rt.pipe_offset)) - float(main_rt.r_outer)) < 1e-15
         for key, tol in (("pipe_x", 1e-15), ("pipe_z", 1e-15), ("lens_2_x", 1e-14), ("lens_2_z", 1e-14)):
             a, b = res[key], rays[key][i]
             assert np.array_equal(np.isnan(a), np.isnan(b))
-            assert np.nanmax(np.abs(a - b)[~grazing]) <= tol
-            assert np.nanmax(np.abs(a - b)) <= 1e-9
+            d = np.nan_to_num(np.abs(a - b))
+            if degenerate:
+                assert (d > 1e-12).sum() <= 1 and d.max() <= 1e-9, (key, i)
+            else:
+                assert d.max() <= tol, (key, i, float(d.max()))
         a, b = res["target_x"], rays["target_x"][i]
         ok = ~np.isnan(b)
         assert np.array_equal(np.isnan(a), ~ok)

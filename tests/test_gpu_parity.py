@@ -40,9 +40,17 @@ def test_fixture_sweep_bit_exact_vs_twin_and_within_tol_vs_reference(engine, gol
     assert np.array_equal(t.records["idx"], idx)
     assert np.array_equal(t.tof, tof.T)
     # independent libm oracle: indices equal, times within tolerance
-    tof2, k_hit2, idx2 = oracle_libm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a, want_idx=True)
+    tof2, k_hit2, idx2, margin2 = oracle_libm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a, want_idx=True,
+                                                    want_margin=True)
     assert np.array_equal(t.k_hit, k_hit2.T)
     assert np.abs(t.tof - tof2.T).max() <= TOF_TOL
+    # ... and idx, ray by ray: identical wherever the oracle's own decision is not rounding noise (its two deciding
+    # diffs exceed 1e-13 m); what differs sits in the 12 degenerate geometries and is counted
+    from test_gpu_configs import assert_idx_agrees
+    n_noise = assert_idx_agrees(t.records["idx"], idx2, margin2, max_noise_frac=2e-2, what="fixture sweep")
+    degenerate = (offsets == 0) | ((radii == 0.01) & (np.abs(offsets) == 0.01))
+    assert np.array_equal(t.records["idx"][~degenerate], idx2[~degenerate])
+    print(f"fixture sweep: {n_noise} of {idx2.size} rays differ from the libm oracle in idx, all below the noise floor")
     # the reference's fixture database_2.csv and the live reference
     db, sw = golden["database_2"], golden["sweep"]
     assert np.array_equal(t.hit, db["hitted"].reshape(210, 65))
@@ -95,9 +103,12 @@ def test_random_geometries_bit_exact(engine, oracle_dm, oracle_libm):
     assert np.array_equal(t.records["idx"], idx)
     assert np.array_equal(t.k_hit, k_hit.T)
     assert np.array_equal(t.tof, tof.T)
-    tof2, k_hit2, _ = oracle_libm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a)
+    tof2, k_hit2, idx2, margin2 = oracle_libm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a, want_idx=True,
+                                                    want_margin=True)
     assert np.array_equal(t.k_hit, k_hit2.T)
     assert np.abs(t.tof - tof2.T).max() <= TOF_TOL
+    from test_gpu_configs import assert_idx_agrees
+    assert_idx_agrees(t.records["idx"], idx2, margin2, what="random geometries")
 
 
 def test_off_centre_shooters(engine, golden, oracle_dm):

@@ -97,11 +97,43 @@ def test_vector_form_other_materials_and_lenses(oracle_dm, oracle_libm):
             t1, k1, i1 = oracle_dm.table(*args, rtol=rtol, atol=atol, want_idx=True)
         finally:
             oracle_dm.set_math(False)
-        tl, kl, il = oracle_libm.table(*args, rtol=rtol, atol=atol, want_idx=True)
+        tl, kl, il, margin = oracle_libm.table(*args, rtol=rtol, atol=atol, want_idx=True, want_margin=True)
         assert np.array_equal(k1, kl), i
         hit = k1 >= 0
         n_hits += int(hit.sum())
         if hit.any():
             assert np.abs(t1 - tl)[hit].max() < 1e-12
-        assert (i1 != il).mean() < 2e-3      # the index only differs where the decision is rounding noise
+        # the index may only differ where the libm oracle's own decision is rounding noise: ray by ray, its two
+        # deciding diffs must both sit below the 1e-13 m floor; and such rays are rare
+        differs = i1 != il
+        assert not (differs & (margin > 1e-13)).any(), (i, int((differs & (margin > 1e-13)).sum()))
+        assert differs.mean() < 2e-3
     assert n_hits > 1000
+
+
+def test_oracles_against_the_live_reference_with_a_128_element_array(oracle_dm, oracle_libm, golden_array128):
+    """BASELINE configs 3/4 (E = 129): the libm oracle and both forms of the twin against the UNMODIFIED reference
+    run with num_elements = 128 on 96 geometries of the 1024 x 1024 grid (tests/golden/array128.npz)."""
+    gd = golden_array128
+    x_a, z_a = rs.transducer(num_elements=128)
+    alpha, zf = rs.launch_angles(), rs.focus_line()
+    assert np.array_equal(x_a, gd["x_a"]) and np.array_equal(alpha, gd["alpha"])
+    radii, offsets = rs.synthetic_grid(1024, 1024)
+    flat = gd["flat_index"]
+    assert np.array_equal(radii[flat], gd["radius"]) and np.array_equal(offsets[flat], gd["offset"])
+    p = oracle_libm.params()
+    args = (p, radii[flat], offsets[flat], x_a[64], z_a[64], zf, alpha, x_a)
+    ridx = gd["idx"].astype(np.int32)                     # reference encoding: -1 no sign change, -2 NaN line
+    tables = [oracle_libm.table(*args, want_idx=True), oracle_dm.table(*args, want_idx=True)]
+    try:
+        oracle_dm.set_math(True)
+        tables.append(oracle_dm.table(*args, want_idx=True))
+    finally:
+        oracle_dm.set_math(False)
+    for tof, k_hit, idx in tables:
+        assert np.array_equal(k_hit.T, gd["k_hit"])
+        assert np.abs(tof.T - gd["tof"]).max() < 1e-12
+        gi = np.where(idx < -1, -1, idx)
+        differs = (gi != ridx) & (ridx != -2)
+        assert not (differs & (gd["margin"] > 1e-13)).any()
+        assert differs.sum() <= 2e-3 * ridx.size
