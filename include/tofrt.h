@@ -230,6 +230,8 @@ int tofrt_debug_search_host(tofrt_ctx *ctx, const double *m, const double *b, lo
  * instructions per second (thread-level) of a DFMA stream and of the un-fused
  * DMUL+DADD stream the search loop issues (SURVEY.md section 8 d). */
 int tofrt_measure_fp64_peak(tofrt_ctx *ctx, double *dfma_per_s, double *dmul_dadd_per_s);
+/* The same for the FP32 mode (tofrt_table_f32_dev): FFMA stream and un-fused FMUL+FADD stream. */
+int tofrt_measure_fp32_peak(tofrt_ctx *ctx, double *ffma_per_s, double *fmul_fadd_per_s);
 
 /* Kernel-side facts for benchmarks/tests. */
 int tofrt_kernel_info(tofrt_ctx *ctx, int *grid, int *block, int *smem_bytes, int *regs);

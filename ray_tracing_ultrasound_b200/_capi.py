@@ -30,7 +30,7 @@ class RayRecords(ctypes.Structure):
 
 
 EXPORTS = ["tofrt_version", "tofrt_last_error", "tofrt_device_count", "tofrt_create", "tofrt_destroy",
-           "tofrt_setup", "tofrt_setup_shooters", "tofrt_set_option", "tofrt_get_info", "tofrt_last_stats", "tofrt_lens_host", "tofrt_table_dev", "tofrt_table_f32_dev", "tofrt_table_host", "tofrt_host_alloc", "tofrt_host_free", "tofrt_hits_host", "tofrt_debug_search_host", "tofrt_fermat_dev", "tofrt_fermat_host", "tofrt_fermat3d_setup", "tofrt_fermat3d_dev", "tofrt_fermat3d_host", "tofrt_kernel_info", "tofrt_measure_fp64_peak"]
+           "tofrt_setup", "tofrt_setup_shooters", "tofrt_set_option", "tofrt_get_info", "tofrt_last_stats", "tofrt_lens_host", "tofrt_table_dev", "tofrt_table_f32_dev", "tofrt_table_host", "tofrt_host_alloc", "tofrt_host_free", "tofrt_hits_host", "tofrt_debug_search_host", "tofrt_fermat_dev", "tofrt_fermat_host", "tofrt_fermat3d_setup", "tofrt_fermat3d_dev", "tofrt_fermat3d_host", "tofrt_kernel_info", "tofrt_measure_fp64_peak", "tofrt_measure_fp32_peak"]
 
 _lib = None
 
@@ -89,6 +89,7 @@ def load():
                                         ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.tofrt_kernel_info.argtypes = [ctypes.c_void_p] + [c_int_p] * 4
     lib.tofrt_measure_fp64_peak.argtypes = [ctypes.c_void_p, c_double_p, c_double_p]
+    lib.tofrt_measure_fp32_peak.argtypes = [ctypes.c_void_p, c_double_p, c_double_p]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

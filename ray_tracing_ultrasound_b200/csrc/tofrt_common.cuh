@@ -24,7 +24,7 @@ constexpr int kThreadsGuided = TOFRT_THREADS_GUIDED;
 #endif
 constexpr int kChunk = TOFRT_SCAN_CHUNK;  // lens samples per early-exit check of the literal scan (<= 32)
 constexpr int kNoHit = 0x7fffffff;
-// per-ray tables of the FP64 table kernel as planes: ray_t[shooter][plane][r], r < 32 C, holds ray min(r, K-1)
+// per-ray tables of the FP64 table kernel: ray_t[shooter][c][plane][lane] holds ray min(32 c + lane, K-1)
 enum { kPlaneXp, kPlaneZp, kPlaneCpq, kPlaneSpq, kPlaneZf, kPlaneApq, kPlaneBpq, kPlanePhi, kRayPlanes };
 // executed-work counters of the instrumented (STATS) instantiation, per thread-ray (tofrt_last_stats)
 enum { kStRays, kStBracket, kStProbes, kStDiffs, kStLens2, kStLanding, kStCand, kStWinners, kStFallback, kStScan,
@@ -46,7 +46,7 @@ struct DevSetup {
     double rx_min, rx_max;                   // finite receiver range
     int K, Npad, E, E_sorted, has_nonfinite_rx, tables_ok;
     int C;                 // 32-ray chunks per shot: ceil(K / 32)
-    const double *ray_t;   // [S][kRayPlanes][32 C] per-ray tables, padded with copies of the last ray
+    const double *ray_t;   // [S][C][kRayPlanes][32] per-ray tables, padded with copies of the last ray
     double2 P0, PN;        // first and last lens sample (the guided search tests them for every ray)
     int chords_plain;    // 1: abscissae strictly increasing and no chord is np.isclose-vertical (main_rt.py:110): checked per setup
     int hits_in_global;  // 1: E too large for the per-warp shared-memory first-hit state -> keep it in the output rows
@@ -81,6 +81,12 @@ struct TableArgs {
     int any_rec;           // any per-ray record requested (besides legs)
     int s_begin, s_count;  // shooters [s_begin, s_begin + s_count) of the setup; outputs are [s_count][G][...]
     const double *inject_m, *inject_b;  // test hook (tofrt_debug_search_host): replace the reflected line of ray [w][k]
+    // sparse emission (tofrt_hits_host): when hit_slots is set the warp writes the hits of its row, ordered by
+    // receiver, into the row's slot of hit_cap (e, k, tof) entries and their number into hit_count[row]; the dense
+    // row is then not stored (a row with more than hit_cap hits only counts: the host falls back to the dense path)
+    uint4 *hit_slots;
+    int *hit_count;
+    int hit_cap;
     unsigned long long *counter;
     unsigned long long *stats;  // [kNumStats] executed-work counters (instrumented instantiation only)
 };

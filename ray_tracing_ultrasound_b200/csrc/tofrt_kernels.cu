@@ -104,6 +104,8 @@ table_kernel_t pick_table_kernel(bool hg, bool guided, bool flat, bool vec, bool
 // variables).  The per-function opt-in attribute is per DEVICE, not per context, so it is always raised to this
 // maximum: two live contexts with different K / E on one GPU can then never lower each other's limit.
 constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;
+constexpr int kHitSlotCap = 16;              // (e, k, tof) entries per row slot of the fused sparse emission
+constexpr size_t kHitChunkRows = 131072;     // rows per pipelined chunk of tofrt_hits_host (32 MB of slots)
 constexpr unsigned kCounterSlots = 64, kCounterStride = 16;  // 128 B per slot: [0] work counter, [1..] statistics
 
 struct tofrt_ctx {
@@ -151,6 +153,15 @@ struct tofrt_ctx {
     // tofrt_hits_host workspace (grow-only): dense intermediate, counts/offsets, scan scratch, hit list
     void *hw[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t hw_bytes[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // fused sparse emission (tofrt_hits_host): geometries + two pipeline slots
+    double *he_in = nullptr; size_t he_in_bytes = 0;
+    uint4 *he_slots[2] = {nullptr, nullptr};
+    int *he_cnt[2] = {nullptr, nullptr}, *he_flag[2] = {nullptr, nullptr};
+    long long *he_cnt64[2] = {nullptr, nullptr}, *he_off[2] = {nullptr, nullptr};
+    void *he_tmp[2] = {nullptr, nullptr}, *he_list[2] = {nullptr, nullptr};
+    size_t he_bytes[2][7] = {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
+    long long *he_total = nullptr;   // pinned: per slot (hits in the chunk, overflow flag)
+    cudaEvent_t ev_cnt[2] = {nullptr, nullptr};
     double *d_d1 = nullptr;   // Fermat solver: |A_e - P_j|/c1, built lazily per setup
     // 3-D two-point solve (tofrt_fermat3d_setup)
     bool f3_ready = false;
@@ -210,6 +221,13 @@ int tofrt_destroy(tofrt_ctx *c)
     cudaFree(c->ws[0]); cudaFree(c->ws[1]); cudaFree(c->d_in); cudaFree(c->d_d1);
     cudaFree(c->f3_geo); cudaFree(c->f3_smp);
     for (int i = 0; i < 10; ++i) cudaFree(c->hw[i]);
+    cudaFree(c->he_in);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->he_slots[i]); cudaFree(c->he_cnt[i]); cudaFree(c->he_flag[i]); cudaFree(c->he_cnt64[i]);
+        cudaFree(c->he_off[i]); cudaFree(c->he_tmp[i]); cudaFree(c->he_list[i]);
+        if (c->ev_cnt[i]) cudaEventDestroy(c->ev_cnt[i]);
+    }
+    if (c->he_total) cudaFreeHost(c->he_total);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
@@ -528,14 +546,21 @@ int tofrt_lens_host(tofrt_ctx *c, double *lens_x, double *lens_z)
     return TOFRT_OK;
 }
 
+struct HitEmit {  // sparse emission of table_dev_impl: per-row slots instead of the dense rows
+    uint4 *slots = nullptr;
+    int *count = nullptr;
+    int cap = 0;
+};
+
 static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_offset, long long G, double *d_tof,
                           int *d_k_hit, const tofrt_ray_records *d_rec, void *stream, int s_begin, int s_count,
-                          const double *inject_m = nullptr, const double *inject_b = nullptr)
+                          const double *inject_m = nullptr, const double *inject_b = nullptr,
+                          const HitEmit *emit = nullptr)
 {
     if (!c || G < 0) return fail(TOFRT_E_BADARG, "tofrt_table_dev: bad argument");
     if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_table_dev: call tofrt_setup first");
     if (G == 0) return TOFRT_OK;
-    if (!d_radius || !d_offset || !d_tof || !d_k_hit) return fail(TOFRT_E_BADARG, "tofrt_table_dev: NULL buffer");
+    if (!d_radius || !d_offset || ((!d_tof || !d_k_hit) && !emit)) return fail(TOFRT_E_BADARG, "tofrt_table_dev: NULL buffer");
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     TableArgs T{};
@@ -544,6 +569,7 @@ static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_
     T.any_rec = T.rec.pipe_x || T.rec.pipe_z || T.rec.lens2_x || T.rec.lens2_z || T.rec.target_x || T.rec.idx;
     T.s_begin = s_begin; T.s_count = s_count;
     T.inject_m = inject_m; T.inject_b = inject_b;
+    if (emit) { T.hit_slots = emit->slots; T.hit_count = emit->count; T.hit_cap = emit->cap; }
     cudaError_t ce;
     T.counter = c->take_counter(st, &ce);
     CUDA_TRY(ce);
@@ -755,8 +781,10 @@ void tofrt_host_free(void *p)
     if (p) cudaFreeHost(p);
 }
 
-int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, long long G, long long capacity,
-                    int *hit_g, int *hit_e, int *hit_k, double *hit_tof, long long *n_hits)
+// Dense route to the hit list (many receivers per row, or a row that overflowed its slot): full table on the device,
+// count per row -> exclusive scan -> ordered compaction.
+static int hits_host_dense(tofrt_ctx *c, const double *radius, const double *offset, long long G, long long capacity,
+                           int *hit_g, int *hit_e, int *hit_k, double *hit_tof, long long *n_hits)
 {
     if (!c || G < 0 || capacity < 0 || !n_hits) return fail(TOFRT_E_BADARG, "tofrt_hits_host: bad argument");
     if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_hits_host: call tofrt_setup first");
@@ -834,6 +862,122 @@ int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, lo
     }
     cleanup();
 #undef TRY_H
+    if (total > capacity) return fail(TOFRT_E_TOOLARGE, "tofrt_hits_host: capacity too small (n_hits holds the required size)");
+    return TOFRT_OK;
+}
+
+// Hit list through the fused emission: the table kernel writes each row's hits into a small per-row slot (no dense
+// table is stored or re-read); per chunk of rows a scan of the counts and an ordered gather build the list, and the
+// list of chunk i travels to the host while chunk i+1 is traced (two slots, two streams, as tofrt_table_host).
+int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, long long G, long long capacity,
+                    int *hit_g, int *hit_e, int *hit_k, double *hit_tof, long long *n_hits)
+{
+    if (!c || G < 0 || capacity < 0 || !n_hits) return fail(TOFRT_E_BADARG, "tofrt_hits_host: bad argument");
+    if (!c->ready) return fail(TOFRT_E_NOSETUP, "tofrt_hits_host: call tofrt_setup first");
+    *n_hits = 0;
+    if (G == 0) return TOFRT_OK;
+    if (!radius || !offset || (capacity > 0 && (!hit_g || !hit_e || !hit_k || !hit_tof)))
+        return fail(TOFRT_E_BADARG, "tofrt_hits_host: NULL buffer");
+    if (c->S.hits_in_global)  // the first-hit state lives in the dense rows: nothing to fuse
+        return hits_host_dense(c, radius, offset, G, capacity, hit_g, hit_e, hit_k, hit_tof, n_hits);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t g = (size_t)G, NSH = (size_t)c->n_shooters;
+    const int cap = kHitSlotCap;
+    const size_t chunk = std::min<size_t>(g, kHitChunkRows);
+    const size_t n_chunks = (g + chunk - 1) / chunk;
+    if (!c->s_compute) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        }
+    }
+    // grow-only workspace: geometries, and per pipeline slot the row slots, counts, offsets, scan scratch, list, total
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (long long *)nullptr, (long long *)nullptr, (int)(chunk + 1)));
+    auto grow = [&](void **q, size_t *have, size_t bytes) {
+        bytes = std::max<size_t>(bytes, 16);
+        if (*have >= bytes) return cudaSuccess;
+        cudaFree(*q); *q = nullptr; *have = 0;
+        cudaError_t e = cudaMalloc(q, bytes);
+        if (e == cudaSuccess) *have = bytes;
+        return e;
+    };
+    const size_t list_cap = chunk * (size_t)cap;  // most hits one chunk can deliver through the slots
+    CUDA_TRY(grow((void **)&c->he_in, &c->he_in_bytes, sizeof(double) * 2 * g));
+    for (int s = 0; s < 2; ++s) {
+        CUDA_TRY(grow((void **)&c->he_slots[s], &c->he_bytes[s][0], sizeof(uint4) * list_cap));
+        CUDA_TRY(grow((void **)&c->he_cnt[s], &c->he_bytes[s][1], sizeof(int) * chunk));
+        CUDA_TRY(grow((void **)&c->he_cnt64[s], &c->he_bytes[s][2], sizeof(long long) * (chunk + 1)));
+        CUDA_TRY(grow((void **)&c->he_off[s], &c->he_bytes[s][3], sizeof(long long) * (chunk + 1)));
+        CUDA_TRY(grow((void **)&c->he_tmp[s], &c->he_bytes[s][4], tmp_bytes));
+        CUDA_TRY(grow((void **)&c->he_list[s], &c->he_bytes[s][5], list_cap * 20));
+        CUDA_TRY(grow((void **)&c->he_flag[s], &c->he_bytes[s][6], sizeof(int)));
+    }
+    if (!c->he_total) CUDA_TRY(cudaHostAlloc((void **)&c->he_total, 4 * sizeof(long long), cudaHostAllocDefault));
+    if (!c->ev_cnt[0]) for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_cnt[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaMemcpyAsync(c->he_in, radius, sizeof(double) * g, cudaMemcpyHostToDevice, c->s_compute));
+    CUDA_TRY(cudaMemcpyAsync(c->he_in + g, offset, sizeof(double) * g, cudaMemcpyHostToDevice, c->s_compute));
+
+    long long total = 0;
+    bool overflow = false;
+    int rc = TOFRT_OK;
+    const size_t n_items = n_chunks * NSH;
+    // drain(i): the host learns chunk i's hit count, then queues its copies at the running offset
+    auto drain = [&](size_t i) -> int {
+        const int slot = (int)(i & 1);
+        CUDA_TRY(cudaEventSynchronize(c->ev_cnt[slot]));
+        const long long got = c->he_total[2 * slot];
+        if (c->he_total[2 * slot + 1]) overflow = true;
+        const long long room = std::max<long long>(0, capacity - total);
+        const size_t n = (size_t)std::min<long long>(got, room);
+        if (n && !overflow) {
+            const char *L = (const char *)c->he_list[slot];
+            CUDA_TRY(cudaStreamWaitEvent(c->s_copy, c->ev_done[slot], 0));
+            CUDA_TRY(cudaMemcpyAsync(hit_g + total, L, sizeof(int) * n, cudaMemcpyDeviceToHost, c->s_copy));
+            CUDA_TRY(cudaMemcpyAsync(hit_e + total, L + 4 * list_cap, sizeof(int) * n, cudaMemcpyDeviceToHost, c->s_copy));
+            CUDA_TRY(cudaMemcpyAsync(hit_k + total, L + 8 * list_cap, sizeof(int) * n, cudaMemcpyDeviceToHost, c->s_copy));
+            CUDA_TRY(cudaMemcpyAsync(hit_tof + total, L + 12 * list_cap, sizeof(double) * n, cudaMemcpyDeviceToHost, c->s_copy));
+        }
+        CUDA_TRY(cudaEventRecord(c->ev_free[slot], c->s_copy));
+        total += got;
+        return TOFRT_OK;
+    };
+    for (size_t i = 0; i < n_items && rc == TOFRT_OK && !overflow; ++i) {
+        const int slot = (int)(i & 1);
+        const int sh = (int)(i / n_chunks);
+        const size_t done = (i % n_chunks) * chunk, n = std::min(chunk, g - done);
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_free[slot], 0));
+        HitEmit em;
+        em.slots = c->he_slots[slot]; em.count = c->he_cnt[slot]; em.cap = cap;
+        rc = table_dev_impl(c, c->he_in + done, c->he_in + g + done, (long long)n, nullptr, nullptr, nullptr,
+                            (void *)c->s_compute, sh, 1, nullptr, nullptr, &em);
+        if (rc != TOFRT_OK) break;
+        char *L = (char *)c->he_list[slot];
+        const int blocks = (int)((n * 32 + 255) / 256);
+        CUDA_TRY(cudaMemsetAsync(c->he_flag[slot], 0, sizeof(int), c->s_compute));
+        tofrt_widen_counts_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c->s_compute>>>(c->he_cnt[slot], (long long)n, c->he_cnt64[slot]);
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->he_tmp[slot], tmp_bytes, c->he_cnt64[slot], c->he_off[slot], (int)n + 1, c->s_compute));
+        tofrt_gather_slots_kernel<<<blocks, 256, 0, c->s_compute>>>(
+            c->he_slots[slot], c->he_cnt[slot], c->he_off[slot], (long long)n, cap, (long long)((size_t)sh * g + done), 0,
+            (long long)list_cap, (int *)L, (int *)(L + 4 * list_cap), (int *)(L + 8 * list_cap),
+            (double *)(L + 12 * list_cap), c->he_flag[slot]);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->s_compute));
+        CUDA_TRY(cudaMemcpyAsync(&c->he_total[2 * slot], c->he_off[slot] + n, sizeof(long long), cudaMemcpyDeviceToHost, c->s_compute));
+        CUDA_TRY(cudaMemcpyAsync(&c->he_total[2 * slot + 1], c->he_flag[slot], sizeof(int), cudaMemcpyDeviceToHost, c->s_compute));
+        CUDA_TRY(cudaEventRecord(c->ev_cnt[slot], c->s_compute));
+        if (i >= 1) rc = drain(i - 1);   // chunk i is queued: now place chunk i-1's copies
+    }
+    if (rc == TOFRT_OK && !overflow && n_items >= 1) rc = drain(n_items - 1);
+    cudaError_t e1 = cudaStreamSynchronize(c->s_compute), e2 = cudaStreamSynchronize(c->s_copy);
+    if (rc != TOFRT_OK) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(TOFRT_E_CUDA, std::string("tofrt_hits_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    if (overflow)  // some row holds more hits than a slot: the dense route handles any number
+        return hits_host_dense(c, radius, offset, G, capacity, hit_g, hit_e, hit_k, hit_tof, n_hits);
+    *n_hits = total;
     if (total > capacity) return fail(TOFRT_E_TOOLARGE, "tofrt_hits_host: capacity too small (n_hits holds the required size)");
     return TOFRT_OK;
 }
@@ -1063,6 +1207,37 @@ int tofrt_measure_fp64_peak(tofrt_ctx *c, double *dfma_per_s, double *dmul_dadd_
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
     *dfma_per_s = best[0];
     *dmul_dadd_per_s = best[1];
+    return TOFRT_OK;
+}
+
+int tofrt_measure_fp32_peak(tofrt_ctx *c, double *ffma_per_s, double *fmul_fadd_per_s)
+{
+    if (!c || !ffma_per_s || !fmul_fadd_per_s) return fail(TOFRT_E_BADARG, "tofrt_measure_fp32_peak: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    float *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(float)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 1 << 15, blocks = c->sm_count * 8, threads = 256;
+    const double inst = (double)blocks * threads * iters * 16.0;
+    double best[2] = {0, 0};
+    for (int mode = 0; mode < 2; ++mode) {
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(e0);
+            if (mode == 0) tofrt_fp32_peak_kernel<0><<<blocks, threads>>>(d_out, iters, 0.999999f, 1e-9f);
+            else tofrt_fp32_peak_kernel<1><<<blocks, threads>>>(d_out, iters, 0.999999f, 1e-9f);
+            cudaEventRecord(e1);
+            cudaError_t e = cudaEventSynchronize(e1);
+            if (e != cudaSuccess) { cudaFree(d_out); return fail(TOFRT_E_CUDA, cudaGetErrorString(e)); }
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0) best[mode] = std::max(best[mode], inst / (ms * 1e-3));
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    *ffma_per_s = best[0];
+    *fmul_fadd_per_s = best[1];
     return TOFRT_OK;
 }
 

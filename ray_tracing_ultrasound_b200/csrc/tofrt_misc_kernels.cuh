@@ -40,6 +40,35 @@ __global__ void tofrt_compact_hits_kernel(const int *k_hit, const double *tof, l
     }
 }
 
+// ---- sparse emission: per-row slots written by the table kernel -> ordered hit list ---------------------
+// cnt[rows] must be followed by one zero entry; off = exclusive scan of cnt (rows + 1 entries, off[rows] = total).
+// flags[0] is raised when a row holds more hits than its slot (the caller then takes the dense path).
+__global__ void tofrt_gather_slots_kernel(const uint4 *slots, const int *cnt, const long long *off, long long rows,
+                                          int cap, long long row0, long long base, long long capacity, int *hit_g,
+                                          int *hit_e, int *hit_k, double *hit_tof, int *flags)
+{
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int n = cnt[row];
+    if (n > cap) { if (lane == 0) atomicOr(flags, 1); return; }
+    const long long o = base + off[row];
+    for (int i = lane; i < n; i += 32) {
+        const uint4 v = slots[(size_t)row * cap + i];
+        const long long j = o + i;
+        if (j < capacity) {
+            hit_g[j] = (int)(row0 + row); hit_e[j] = (int)v.x; hit_k[j] = (int)v.y;
+            hit_tof[j] = __hiloint2double((int)v.w, (int)v.z);
+        }
+    }
+}
+
+__global__ void tofrt_widen_counts_kernel(const int *cnt, long long rows, long long *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= rows) out[i] = i < rows ? (long long)cnt[i] : 0ll;
+}
+
 // ---- FP64 issue-rate micro-benchmark (the roofline denominator, measured on the box) ----
 // 8 independent dependency chains per thread; MODE 0: DFMA, MODE 1: DMUL+DADD (un-fused, as
 // the scan issues them).  Each loop iteration issues 16 FP64 instructions per thread.
@@ -62,3 +91,23 @@ __global__ void __launch_bounds__(256) tofrt_fp64_peak_kernel(double *out, int i
     if (s == 12345.678) out[0] = s;  // keep the chains alive
 }
 
+
+// FP32 twin of the micro-benchmark (roofline denominator of the FP32 mode): MODE 0 FFMA, MODE 1 FMUL+FADD
+template <int MODE>
+__global__ void __launch_bounds__(256) tofrt_fp32_peak_kernel(float *out, int iters, float a, float b)
+{
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (MODE == 0) { v[i] = fmaf(v[i], a, b); v[i] = fmaf(v[i], a, b); }
+            else { v[i] = __fmul_rn(v[i], a); v[i] = __fadd_rn(v[i], b); }
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    if (s == 12345.678f) out[0] = s;  // keep the chains alive
+}

@@ -43,25 +43,25 @@ __global__ void tofrt_chord_kernel(int K, const double2 *lens, double2 *seg)
 }
 
 
-// per-ray tables of the table kernel as planes [shooter][plane][32 C], C = ceil(K / 32): entry r holds ray
-// min(r, K-1) (the padding repeats the last ray, which the kernel treats as one more, idempotent, copy of it),
-// so a warp's load of 32 consecutive rays is one coalesced line and needs no bounds logic
+// per-ray tables of the table kernel, chunk by chunk: ray_t[shooter][c][plane][lane] holds ray min(32 c + lane, K-1)
+// (the padding repeats the last ray, which the kernel treats as one more, idempotent, copy of it), so a warp's
+// loads are coalesced lines at constant offsets from the chunk's base and need no bounds logic
 __global__ void tofrt_ray_table_kernel(DevSetup S, double *ray_t)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long plane = (long long)S.C * 32;
-    if (i >= plane * S.n_shooters) return;
-    const int s = (int)(i / plane), r = (int)(i - (long long)s * plane);
+    const long long per_shot = (long long)S.C * 32;
+    if (i >= per_shot * S.n_shooters) return;
+    const int s = (int)(i / per_shot), r = (int)(i - (long long)s * per_shot), c = r >> 5, lane = r & 31;
     const int k = min(r, S.K - 1);
     const size_t o = (size_t)s * S.K + k;
-    double *dst = ray_t + (size_t)s * kRayPlanes * plane + r;
+    double *dst = ray_t + ((size_t)s * S.C + c) * (kRayPlanes * 32) + lane;
     const double2 pk = S.lens[k];
-    dst[kPlaneXp * plane] = pk.x;
-    dst[kPlaneZp * plane] = pk.y;
-    dst[kPlaneCpq * plane] = S.cpq[o];
-    dst[kPlaneSpq * plane] = S.spq[o];
-    dst[kPlaneZf * plane] = S.z_f[k];
-    dst[kPlaneApq * plane] = S.a_pq[o];
-    dst[kPlaneBpq * plane] = S.b_pq[o];
-    dst[kPlanePhi * plane] = S.phi_pq[o];
+    dst[kPlaneXp * 32] = pk.x;
+    dst[kPlaneZp * 32] = pk.y;
+    dst[kPlaneCpq * 32] = S.cpq[o];
+    dst[kPlaneSpq * 32] = S.spq[o];
+    dst[kPlaneZf * 32] = S.z_f[k];
+    dst[kPlaneApq * 32] = S.a_pq[o];
+    dst[kPlaneBpq * 32] = S.b_pq[o];
+    dst[kPlanePhi * 32] = S.phi_pq[o];
 }

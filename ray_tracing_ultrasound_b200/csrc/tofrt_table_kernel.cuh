@@ -80,7 +80,8 @@ __device__ __forceinline__ void chord_intersection(const double2 *lens, const do
 // 32 c + l (indices beyond K-1 repeat ray K-1, which is idempotent: same landing point, same atomicMin), so the
 // lanes of a warp hold neighbouring rays: they probe neighbouring lens samples (shared-memory broadcast), die
 // together (rays that miss the lens or are totally reflected come in runs) and take the same branches.  The
-// per-ray tables are stored as planes [plane][32 C] (tofrt_ray_table_kernel): every load is one coalesced line.
+// per-ray tables are stored chunk by chunk, [c][plane][32] (tofrt_ray_table_kernel): every load is one coalesced
+// line at a constant offset from the chunk's base.
 // (Measured and rejected: lane l walking the CONSECUTIVE rays l C .. l C + C-1, which predicts the next bracket to
 // +-1 sample from the lane's own previous ray -- the search gets cheaper, but scattered shared-memory probes, the
 // slow paths of the 4 % dead rays now present in every warp and a 2x slower literal scan cost more: 29.8 vs 25.2 ms.)
@@ -127,7 +128,6 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
     tof_t *w_tof = s_tof + (size_t)warp * E;
     khit_t *w_khit = s_khit + (size_t)warp * E;
     const int C = S.C;               // 32-ray chunks per shot
-    const size_t plane = (size_t)C * 32;
     const unsigned FULL = 0xffffffffu;
     tofrt_vec_lens VL = S.VL;  // lens constants of the vector form (uniform)
     VL.flat = FLAT ? 1 : 0;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
         long long g = w, s_local = 0;
         if (T.s_count > 1) { s_local = w / T.G; g = w - s_local * T.G; }  // 64-bit division only when several shooters
         const int shooter = T.s_begin + (int)s_local;
-        const double *ray_t = S.ray_t + (size_t)shooter * kRayPlanes * plane + lane;  // [plane][c][lane]
+        const double *ray_t = S.ray_t + (size_t)shooter * C * (kRayPlanes * 32) + lane;  // [c][plane][lane]
         const double r_outer = T.radius[g], pipe_offset = T.offset[g];
         const double rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset, rsq2 = rsq * rsq;
         if (HG) { w_tof = T.tof + (size_t)w * E; w_khit = T.k_hit + (size_t)w * E; }
@@ -167,22 +167,22 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
         for (int c = 0; c < C; ++c) {
             const int k = min((c << 5) + lane, K - 1);
             // per-ray constants of the shot: one coalesced, L1-resident load per 32 rays
-            const double *rt = ray_t + (size_t)c * 32;
-            const double z_f = __ldg(rt + kPlaneZf * plane);
+            const double *rt = ray_t + c * (kRayPlanes * 32);
+            const double z_f = __ldg(rt + kPlaneZf * 32);
 
             double x_q, z_q;
             double phi_l = 0.0, cl = 0.0, sl = 0.0, m, b;  // reflected direction: angle, or r^2 (cos, sin)
             if (VEC) {
-                const double xp = __ldg(rt + kPlaneXp * plane), zp = __ldg(rt + kPlaneZp * plane);
-                const double cpq = __ldg(rt + kPlaneCpq * plane), spq = __ldg(rt + kPlaneSpq * plane);
+                const double xp = __ldg(rt + kPlaneXp * 32), zp = __ldg(rt + kPlaneZp * 32);
+                const double cpq = __ldg(rt + kPlaneCpq * 32), spq = __ldg(rt + kPlaneSpq * 32);
                 // ---- main_rt.py:351-364 pipe intersection, upper root; :367-376 reflection on the pipe ----
                 tofrt_vec_pipe(xp, zp, cpq, spq, pipe_offset, rsq, &x_q, &z_q);
                 tofrt_vec_reflect(x_q, rsq, cpq, spq, &cl, &sl);
                 m = sl / cl;
                 b = fma(-m, x_q, z_q);
             } else {
-                const double a_pq = __ldg(rt + kPlaneApq * plane), b_pq = __ldg(rt + kPlaneBpq * plane);
-                const double phi_pq = __ldg(rt + kPlanePhi * plane);
+                const double a_pq = __ldg(rt + kPlaneApq * 32), b_pq = __ldg(rt + kPlaneBpq * 32);
+                const double phi_pq = __ldg(rt + kPlanePhi * 32);
                 // ---- main_rt.py:351-364 pipe intersection, upper root ----
                 double A2 = a_pq * a_pq + 1;
                 double B2 = 2 * (a_pq * b_pq - pipe_offset);
@@ -402,12 +402,15 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                     if (lane == src && first != kNoHit) on_sample = first;
                 }
             }
-            double ix = NAN, iz = NAN;
-            if (idx >= 0) {
-                if (S.chords_plain) chord_intersection<true>(s_lens, s_seg, idx, m, b, &ix, &iz);
-                else chord_intersection<false>(s_lens, s_seg, idx, m, b, &ix, &iz);
+            // chord intersection for every lane (a lane without a crossing computes on chord 0 and discards it:
+            // cheaper than a divergent region around a division)
+            double ix, iz;
+            if (S.chords_plain) chord_intersection<true>(s_lens, s_seg, max(idx, 0), m, b, &ix, &iz);
+            else chord_intersection<false>(s_lens, s_seg, max(idx, 0), m, b, &ix, &iz);
+            if (idx < 0) {
+                ix = NAN; iz = NAN;
+                if (on_sample >= 0) { double2 s = s_lens[on_sample]; ix = s.x; iz = s.y; }
             }
-            else if (on_sample >= 0) { double2 s = s_lens[on_sample]; ix = s.x; iz = s.y; }
 
             // ---- main_rt.py:396-405 refraction back into the lens, landing point ----
             // NaN in -> NaN out, so whole 32-ray groups that missed the lens, or are totally
@@ -473,13 +476,21 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 hi = lo;
                 while (hi < S.E_sorted && s_xs[hi] <= th) ++hi;
             }
-            const bool special = S.has_nonfinite_rx && isinf(target_x);
+            bool special = false;
+            if (S.has_nonfinite_rx) special = isinf(target_x);  // uniform: no receiver is infinite in practice
             const bool want_legs = T.rec.legs != nullptr;
             if (__any_sync(FULL, hi > lo || special || want_legs)) {
                 bool mine = false;
-                for (int i = lo; i < hi; ++i) {
-                    if (STATS) st[kStCand] += 1;
-                    if (np_isclose(target_x, s_xs[i], S.rtol, S.atol)) { atomicMin(const_cast<int *>(&w_khit[s_perm[i]]), k); mine = true; }
+                // np.isclose(target_x, x_e): |target_x - x_e| <= atol + rtol |x_e| for a finite x_e (the sorted copy
+                // holds finite receivers only), or equality.  Usually one candidate: straight-line, the rest in a loop.
+                if (hi > lo) {
+                    if (STATS) st[kStCand] += hi - lo;
+                    const double xe = s_xs[lo];
+                    if (fabs(target_x - xe) <= S.atol + S.rtol * fabs(xe) || target_x == xe) {
+                        atomicMin(const_cast<int *>(&w_khit[s_perm[lo]]), k); mine = true;
+                    }
+                    for (int i = lo + 1; i < hi; ++i)
+                        if (np_isclose(target_x, s_xs[i], S.rtol, S.atol)) { atomicMin(const_cast<int *>(&w_khit[s_perm[i]]), k); mine = true; }
                 }
                 if (special) {
                     for (int e = 0; e < E; ++e)
@@ -516,12 +527,32 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 __syncwarp();
             }
         }
-        // ---- one geometry done: coalesced row of the [G][E] table ----
+        // ---- one geometry done: coalesced row of the [G][E] table, or (sparse emission) only its hits ----
         __syncwarp();
-        for (int e = lane; e < E; e += 32) {
-            int kh = w_khit[e];
-            if (!HG) T.tof[(size_t)w * E + e] = w_tof[e];
-            T.k_hit[(size_t)w * E + e] = kh == kNoHit ? -1 : kh;
+        if (!HG && T.hit_slots) {
+            int base = 0;
+            uint4 *slot = T.hit_slots + (size_t)w * T.hit_cap;
+            for (int e0 = 0; e0 < E; e0 += 32) {
+                const int e = e0 + lane;
+                int kh = 0x7fffffff;  // kNoHit
+                if (e < E) kh = w_khit[e];
+                const unsigned hits = __ballot_sync(FULL, kh != 0x7fffffff);
+                if (kh != 0x7fffffff) {
+                    const int pos = base + __popc(hits & ((1u << lane) - 1u));
+                    if (pos < T.hit_cap) {
+                        const double t = w_tof[e];
+                        slot[pos] = make_uint4((unsigned)e, (unsigned)kh, (unsigned)__double2loint(t), (unsigned)__double2hiint(t));
+                    }
+                }
+                base += __popc(hits);
+            }
+            if (lane == 0) T.hit_count[w] = base;
+        } else {
+            for (int e = lane; e < E; e += 32) {
+                int kh = w_khit[e];
+                if (!HG) T.tof[(size_t)w * E + e] = w_tof[e];
+                T.k_hit[(size_t)w * E + e] = kh == kNoHit ? -1 : kh;
+            }
         }
         __syncwarp();
     }

@@ -96,6 +96,20 @@ class TofEngine:
     def _shape(self, G, last):
         return (self.S, G, last) if self.multi else (G, last)
 
+    def _check_out(self, t, shape, dtype, dev, what):
+        """A caller-supplied output tensor must be exactly what the kernel writes: anything else would be an
+        out-of-bounds or mis-typed device write."""
+        if (tuple(t.shape) != tuple(shape) or t.dtype != dtype or not t.is_cuda or t.device != dev or
+                not t.is_contiguous()):
+            raise ValueError(f"{what} must be a contiguous {dtype} CUDA tensor of shape {tuple(shape)} on {dev}")
+        return t
+
+    @staticmethod
+    def _check_records(records):
+        for key in records:
+            if key not in RECORD_KEYS:
+                raise ValueError(f"unknown record {key!r}")
+
     def set_surface(self, kind):
         """'lens' (the reference's constant-TOF lens, default) or 'flat' (plane z = h0; extension).
         Call before setup()."""
@@ -167,6 +181,12 @@ class TofEngine:
         _capi.check(self._lib.tofrt_measure_fp64_peak(self._ctx, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def measure_fp32_peak(self):
+        """FP32 thread-instructions/s of this GPU: (FFMA stream, un-fused FMUL+FADD stream)."""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        _capi.check(self._lib.tofrt_measure_fp32_peak(self._ctx, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     # ---- main_rt.py:464-501, host buffers -------------------------------------
     def tof_table(self, radii, offsets, records=(), out=None):
         """out = (tof, k_hit): preallocated C-contiguous arrays (float64 / int32), e.g. from
@@ -233,8 +253,12 @@ class TofEngine:
             raise ValueError("radii/offsets must live on the engine's device and have the same shape")
         G = radii.numel()
         dev = radii.device
-        tof = out_tof if out_tof is not None else torch.empty(self._shape(G, self.E), dtype=torch.float64, device=dev)
-        k_hit = out_k_hit if out_k_hit is not None else torch.empty(self._shape(G, self.E), dtype=torch.int32, device=dev)
+        shape = self._shape(G, self.E)
+        tof = (self._check_out(out_tof, shape, torch.float64, dev, "out_tof") if out_tof is not None
+               else torch.empty(shape, dtype=torch.float64, device=dev))
+        k_hit = (self._check_out(out_k_hit, shape, torch.int32, dev, "out_k_hit") if out_k_hit is not None
+                 else torch.empty(shape, dtype=torch.int32, device=dev))
+        self._check_records(records)
         rec, out = None, {}
         if records:
             rec = _capi.RayRecords()
@@ -258,9 +282,14 @@ class TofEngine:
         if not (radii.is_cuda and offsets.is_cuda and radii.dtype == torch.float64 and
                 offsets.dtype == torch.float64 and radii.is_contiguous() and offsets.is_contiguous()):
             raise ValueError("radii/offsets must be contiguous float64 CUDA tensors")
+        if radii.device.index != self.device or radii.shape != offsets.shape:
+            raise ValueError("radii/offsets must live on the engine's device and have the same shape")
         G, dev = radii.numel(), radii.device
-        tof = out_tof if out_tof is not None else torch.empty(self._shape(G, self.E), dtype=torch.float32, device=dev)
-        k_hit = out_k_hit if out_k_hit is not None else torch.empty(self._shape(G, self.E), dtype=torch.int32, device=dev)
+        shape = self._shape(G, self.E)
+        tof = (self._check_out(out_tof, shape, torch.float32, dev, "out_tof") if out_tof is not None
+               else torch.empty(shape, dtype=torch.float32, device=dev))
+        k_hit = (self._check_out(out_k_hit, shape, torch.int32, dev, "out_k_hit") if out_k_hit is not None
+                 else torch.empty(shape, dtype=torch.int32, device=dev))
         stream = torch.cuda.current_stream(dev).cuda_stream
         _capi.check(self._lib.tofrt_table_f32_dev(self._ctx, radii.data_ptr(), offsets.data_ptr(), G,
                                                   tof.data_ptr(), k_hit.data_ptr(), ctypes.c_void_p(stream)))
@@ -334,7 +363,10 @@ class TofEngine:
             if not (v.is_cuda and v.dtype == torch.float64 and v.is_contiguous() and v.shape == fx.shape):
                 raise ValueError("fx/fy/fz must be contiguous float64 CUDA tensors of the same shape")
         F, dev, E = fx.numel(), fx.device, self.f3_E
-        tof = out_tof if out_tof is not None else torch.empty((E, F), dtype=torch.float64, device=dev)
+        if fx.device.index != self.device:
+            raise ValueError("fx/fy/fz must live on the engine's device")
+        tof = (self._check_out(out_tof, (E, F), torch.float64, dev, "out_tof") if out_tof is not None
+               else torch.empty((E, F), dtype=torch.float64, device=dev))
         kmin = torch.empty((E, F), dtype=torch.int32, device=dev) if with_kmin else None
         ab = torch.empty((E, F, 2), dtype=torch.float64, device=dev) if with_angles else None
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -346,6 +378,9 @@ class TofEngine:
 
     # ---- main_rt.py:337-441 -----------------------------------------------------
     def shoot_rays(self, r_outer, pipe_offset, with_idx=False, with_legs=False):
+        if self.multi:
+            raise ValueError("shoot_rays is the reference's single-shot call (main_rt.py:481): set up one shooter "
+                             "(scalar x_shooter), or use tof_table(records=...) for full-matrix capture")
         recs = ["pipe_x", "pipe_z", "lens2_x", "lens2_z", "target_x"]
         if with_idx:
             recs.append("idx")

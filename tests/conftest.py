@@ -41,9 +41,11 @@ def oracle_dm():
 @pytest.fixture(scope="session")
 def engine():
     """The product, through the C ABI.  Builds libtofrt.so if the source is newer."""
-    from ray_tracing_ultrasound_b200 import TofEngine, _build
+    from ray_tracing_ultrasound_b200 import TofEngine, _build, _capi
     if _build.is_stale():
         _build.build()
+    if _capi.load().tofrt_device_count() == 0:
+        pytest.skip("no CUDA device: the engine has no CPU fallback (run `pytest -m gpu` on the B200 box)")
     return TofEngine(0)
 
 

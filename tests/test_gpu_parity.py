@@ -207,6 +207,71 @@ def test_device_resident_api_matches_host_api(engine):
     assert torch.equal(td.tof, td2.tof) and torch.equal(td.k_hit, td2.k_hit)
 
 
+def test_device_api_rejects_wrong_outputs_and_unknown_records(engine):
+    """A mis-shaped / mis-typed / non-contiguous output tensor would be an out-of-bounds device write: refuse it."""
+    import torch
+    _std(engine)
+    radii, offsets = rs.synthetic_grid(8, 8)
+    r_d, o_d = torch.from_numpy(radii).cuda(), torch.from_numpy(offsets).cuda()
+    ok_t, ok_k = torch.empty((64, 65), dtype=torch.float64, device="cuda"), torch.empty((64, 65), dtype=torch.int32, device="cuda")
+    engine.tof_table_cuda(r_d, o_d, out_tof=ok_t, out_k_hit=ok_k)
+    for bad_t, bad_k in ((torch.empty((63, 65), dtype=torch.float64, device="cuda"), ok_k),
+                         (torch.empty((64, 65), dtype=torch.float32, device="cuda"), ok_k),
+                         (ok_t, torch.empty((64, 65), dtype=torch.int64, device="cuda")),
+                         (torch.empty((64, 130), dtype=torch.float64, device="cuda")[:, ::2], ok_k),
+                         (torch.empty((64, 65), dtype=torch.float64), ok_k)):
+        with pytest.raises(ValueError):
+            engine.tof_table_cuda(r_d, o_d, out_tof=bad_t, out_k_hit=bad_k)
+    with pytest.raises(ValueError):
+        engine.tof_table_f32_cuda(r_d, o_d, out_tof=ok_t)          # float64 where the FP32 mode writes float32
+    with pytest.raises(ValueError):
+        engine.tof_table_cuda(r_d, o_d, records=("idx", "no_such_record"))
+    x_a, z_a = rs.transducer()
+    engine.setup(rs.launch_angles(), rs.focus_line(), x_a[:3], z_a[:3], x_a)
+    with pytest.raises(ValueError):
+        engine.shoot_rays(0.05, 0.0)                               # several shooters: not the single-shot call
+    torch.cuda.synchronize()
+
+
+def test_calls_in_flight_on_two_streams_do_not_share_a_work_counter(engine):
+    """Every launch draws its own work-counter slot: two table calls queued back to back on different streams (and a
+    host-buffer call on the library's own streams) must each produce complete, identical tables."""
+    import torch
+    _std(engine)
+    radii, offsets = rs.synthetic_grid(256, 64)
+    r_d, o_d = torch.from_numpy(radii).cuda(), torch.from_numpy(offsets).cuda()
+    ref = engine.tof_table_cuda(r_d, o_d)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for rep in range(4):
+        with torch.cuda.stream(s1):
+            a = engine.tof_table_cuda(r_d, o_d)
+        with torch.cuda.stream(s2):
+            b = engine.tof_table_cuda(r_d, o_d)
+        outs += [a, b]
+    th = engine.tof_table(radii[:4096], offsets[:4096])            # runs on the context's own non-blocking streams
+    torch.cuda.synchronize()
+    for t in outs:
+        assert torch.equal(t.tof, ref.tof) and torch.equal(t.k_hit, ref.k_hit)
+    assert np.array_equal(th.tof, ref.tof[:4096].cpu().numpy())
+
+
+def test_two_engines_with_different_sizes_on_one_gpu(engine):
+    """The opt-in shared-memory limit is per kernel and per DEVICE: a second, smaller setup on another context must
+    not lower it under a live, larger one (main_rt's K = 905 engine next to main_compare's K = 1810 one)."""
+    from ray_tracing_ultrasound_b200 import TofEngine
+    x_a, z_a = rs.transducer()
+    big = TofEngine(0).setup(rs.launch_angles(4096), rs.focus_line(4096), x_a[32], z_a[32], x_a)
+    small = TofEngine(0).setup(rs.launch_angles(64), rs.focus_line(64), x_a[32], z_a[32], x_a)
+    radii, offsets = rs.synthetic_grid(6, 6)
+    a = big.tof_table(radii, offsets)
+    b = small.tof_table(radii, offsets)
+    a2 = big.tof_table(radii, offsets)
+    assert np.array_equal(a.tof, a2.tof) and np.array_equal(a.k_hit, a2.k_hit) and b.tof.shape == (36, 65)
+    big.close(); small.close()
+
+
 def test_full_size_grid_properties(engine, oracle_dm):
     """BASELINE config 3 at full size (129 receivers, 1024 x 1024 geometries): the table is
     checked through size-independent properties -- a random subsample against the oracle,
