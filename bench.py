@@ -455,6 +455,32 @@ def main():
         }
         del tof32, kh32, h64, h32, both, same_ray, dts
 
+        # ---- BASELINE config 1 (the reference's own 210-geometry sweep) and 1b (main_compare.py's single K = 1810
+        #      shot): latency of one table call, device-resident, small-G mode on (default) and off ----
+        if rank == 0:
+            small = {}
+            xa1, za1 = rs.transducer()
+            for name, kk, (rr, oo) in (("config1_210_geometries_K905", 905, rs.sweep_grid()),
+                                       ("config1b_1_geometry_K1810", 1810, (np.array([0.037]), np.array([0.0038])))):
+                e1 = TofEngine(local).setup(rs.launch_angles(kk), rs.focus_line(kk), xa1[32], za1[32], xa1)
+                r1, o1 = torch.from_numpy(np.ascontiguousarray(rr)).to(dev), torch.from_numpy(np.ascontiguousarray(oo)).to(dev)
+                t1 = torch.empty((len(rr), 65), dtype=torch.float64, device=dev)
+                k1 = torch.empty((len(rr), 65), dtype=torch.int32, device=dev)
+                res = {}
+                for mode in (True, False):
+                    e1.set_small_g(mode)
+                    call = lambda: e1.tof_table_cuda(r1, o1, out_tof=t1, out_k_hit=k1)
+                    for _ in range(5):
+                        call()
+                    torch.cuda.synchronize()
+                    res["small_g_on_us" if mode else "small_g_off_us"] = timed(call, 50) * 1e3
+                res["ray_solves_per_s"] = 65 * len(rr) / (res["small_g_on_us"] * 1e-6)
+                small[name] = res
+                e1.close()
+            small["note"] = ("one tofrt_table_dev call incl. launch, back to back on one stream; config 1b has 57 chunks per "
+                             "shot (> 32 warps), so it always takes the regular kernel")
+            extras["small_configs"] = small
+
         # ---- 3-D two-point solve (BASELINE config 5, extension -- parity unpinned), reported separately ----
         if rank == 0 and not args.no_3d:
             gm = (np.arange(32) - 15.5) * float(rs.PITCH)                   # 32 x 32 matrix array
@@ -577,6 +603,8 @@ def main():
                              "frac_vs_reference_algorithm": ops_ref / (f["kernel_ms"] * 1e-3) / peak32_issue,
                              "peak_source": "tofrt_measure_fp32_peak on this GPU (un-fused FMUL+FADD thread-instructions/s)"}
             out["fp32"] = f
+        if "small_configs" in extras:
+            out["small_configs"] = extras["small_configs"]
         if "fermat3d" in extras:
             out["fermat3d"] = extras["fermat3d"]
         if gather_info:

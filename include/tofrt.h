@@ -145,6 +145,12 @@ int tofrt_get_info(tofrt_ctx *ctx, int what);
  * O(N) scan (guided mode: undecidable rays; 0 in every run so far), [10] rays that ran the |diff| <= 1e-8 on-sample rule.
  * Entries beyond TOFRT_NUM_STATS are zero.  With statistics off the counters read zero. */
 #define TOFRT_OPT_STATS 4
+/* Small-G latency mode (default 1 = automatic): a call with fewer (shooter, geometry) items than half the GPU's
+ * resident warps -- main_rt.py's own 210-geometry sweep, main_compare.py's single geometry -- runs one CTA per item
+ * with one 32-ray chunk per warp and a CTA-wide first-hit reduction, instead of one warp per item walking its
+ * ceil(K / 32) chunks serially (needs ceil(K / 32) <= 32, the guided search and the shared-memory receiver budget;
+ * otherwise the call silently takes the regular kernel).  Same results, bit for bit.  0 switches it off. */
+#define TOFRT_OPT_SMALL_G 5
 #define TOFRT_NUM_STATS 11
 int tofrt_last_stats(tofrt_ctx *ctx, unsigned long long *stats, int n);
 

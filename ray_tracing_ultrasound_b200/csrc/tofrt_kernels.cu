@@ -121,6 +121,7 @@ struct tofrt_ctx {
     double *d_alpha = nullptr, *d_zf = nullptr, *d_a = nullptr, *d_b = nullptr, *d_phi = nullptr, *d_leg1 = nullptr;
     double *d_cs = nullptr;   // cos / sin of phi_pq, [2][S*K]
     double *d_ray_t = nullptr;  // per-ray tables of the table kernel as coalesced planes
+    int opt_small_g = 1;        // 1: few geometries run a CTA per geometry (TOFRT_OPT_SMALL_G)
     int opt_stats = 0;          // 1: table calls run the instrumented instantiation (tofrt_last_stats)
     double2 *d_lens = nullptr, *d_seg = nullptr;
     int opt_guided = 1;
@@ -145,7 +146,10 @@ struct tofrt_ctx {
         return p;
     }
     // host-buffer pipeline (tofrt_table_host)
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    // s_compute / s_compute2: one compute stream per pipeline slot, so that chunk i+1's kernel fills the SMs chunk i's
+    // last CTAs leave idle instead of waiting for its tail; s_copy: device -> host; s_h2d: the chunks' geometries
+    cudaStream_t s_compute = nullptr, s_compute2 = nullptr, s_copy = nullptr, s_h2d = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     void *ws[2] = {nullptr, nullptr};
     size_t ws_bytes = 0, in_cap = 0;
@@ -233,7 +237,10 @@ int tofrt_destroy(tofrt_ctx *c)
         if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]);
     }
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_compute2) cudaStreamDestroy(c->s_compute2);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    for (int i = 0; i < 2; ++i) if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     delete c;
     return TOFRT_OK;
 }
@@ -472,6 +479,10 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
             for (int stt = 0; stt < 2; ++stt)
                 CUDA_TRY(cudaFuncSetAttribute(pick_table_kernel(hg, gd != 0, flat, vec != 0, stt != 0),
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, true, false, true, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel<false, true, false, false, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     int occ = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pick_table_kernel(hg, !flat, flat, c->opt_vector != 0),
                                                              flat ? kThreads : kThreadsGuided, flat ? smem : smem_guided));
@@ -497,6 +508,11 @@ int tofrt_set_option(tofrt_ctx *c, int option, int value)
             return fail(TOFRT_E_BADARG, "tofrt_set_option: bad math mode");
         c->opt_vector = value;
         c->S.vector_math = value;
+        return TOFRT_OK;
+    }
+    if (option == TOFRT_OPT_SMALL_G) {
+        if (value != 0 && value != 1) return fail(TOFRT_E_BADARG, "tofrt_set_option: bad small-G switch");
+        c->opt_small_g = value;
         return TOFRT_OK;
     }
     if (option == TOFRT_OPT_STATS) {
@@ -580,6 +596,18 @@ static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_
     const int threads = guided ? kThreadsGuided : kThreads, wpc = threads / 32;
     const size_t smem = guided ? c->smem_guided : c->smem;
     int grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, (warps_needed + wpc - 1) / wpc);
+    // Small-G latency mode: with fewer (shooter, geometry) items than the GPU has resident warps, a warp per item
+    // leaves most of the machine idle while each warp walks its 29 chunks one after the other; a CTA per item with a
+    // chunk per warp finishes an item in the time of ONE chunk.  (Test hook and instrumented runs keep the main kernel.)
+    const bool split = guided && !c->S.hits_in_global && !c->opt_stats && !inject_m && c->opt_small_g &&
+                       c->S.C <= kThreadsGuided / 32 && warps_needed < (long long)c->sm_count * c->ctas_per_sm * wpc / 2;
+    if (split) {
+        grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, warps_needed);
+        if (c->S.vector_math) tofrt_table_kernel<false, true, false, true, false, true><<<grid, threads, smem, st>>>(c->S, T);
+        else tofrt_table_kernel<false, true, false, false, false, true><<<grid, threads, smem, st>>>(c->S, T);
+        CUDA_TRY(cudaGetLastError());
+        return TOFRT_OK;
+    }
     // (flat interface, extension: a plane has no strict curvature, so `guided` is false there: literal scan only)
     pick_table_kernel(c->S.hits_in_global != 0, guided, c->S.surface != 0, c->S.vector_math != 0, c->opt_stats != 0)
         <<<grid, threads, smem, st>>>(c->S, T);
@@ -615,6 +643,24 @@ int tofrt_table_f32_dev(tofrt_ctx *c, const double *d_radius, const double *d_of
     return TOFRT_OK;
 }
 
+static int ensure_streams(tofrt_ctx *c)
+{
+    if (!c->s_compute) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        }
+    }
+    if (!c->s_compute2) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute2, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+    }
+    return TOFRT_OK;
+}
+
 // Host-buffer path: the geometries are cut into chunks whose outputs are ~64 MB; chunk i is
 // traced on one stream into one of two device slots while the results of chunk i-1 travel to the
 // host on a second stream (pinned host buffers make that copy truly asynchronous), so the
@@ -645,14 +691,7 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
     const size_t slot_bytes = chunk * per_geom + 16 * 256;
 
     // grow-only workspace
-    if (!c->s_compute) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
-        }
-    }
+    { int rcs = ensure_streams(c); if (rcs != TOFRT_OK) return rcs; }
     if (c->ws_bytes < slot_bytes) {
         for (int i = 0; i < 2; ++i) { cudaFree(c->ws[i]); c->ws[i] = nullptr; }
         c->ws_bytes = 0;
@@ -664,8 +703,6 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
         CUDA_TRY(cudaMalloc(&c->d_in, sizeof(double) * 2 * g));
         c->in_cap = 2 * g;
     }
-    CUDA_TRY(cudaMemcpyAsync(c->d_in, radius, sizeof(double) * g, cudaMemcpyHostToDevice, c->s_compute));
-    CUDA_TRY(cudaMemcpyAsync(c->d_in + g, offset, sizeof(double) * g, cudaMemcpyHostToDevice, c->s_compute));
 
     int rc = TOFRT_OK;
     const size_t n_chunks = (g + chunk - 1) / chunk;
@@ -689,11 +726,22 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
         if (R.target_x) d.target_x = (double *)take(n * K * sizeof(double));
         if (R.idx) d.idx = (int *)take(n * K * sizeof(int));
         if (R.legs) d.legs = (double *)take(n * K * 4 * sizeof(double));
-        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_free[slot], 0));
+        cudaStream_t cs = slot ? c->s_compute2 : c->s_compute;
+        if (sh == 0) {  // this chunk's geometries (every shooter reuses them)
+            CUDA_TRY(cudaMemcpyAsync(c->d_in + done, radius + done, sizeof(double) * n, cudaMemcpyHostToDevice, c->s_h2d));
+            CUDA_TRY(cudaMemcpyAsync(c->d_in + g + done, offset + done, sizeof(double) * n, cudaMemcpyHostToDevice, c->s_h2d));
+            CUDA_TRY(cudaEventRecord(c->ev_in[slot], c->s_h2d));
+            CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_in[slot], 0));
+        } else if (done == 0) {  // next shooter: both compute streams must have seen every geometry copy
+            CUDA_TRY(cudaEventRecord(c->ev_in[0], c->s_h2d));
+            CUDA_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_in[0], 0));
+            CUDA_TRY(cudaStreamWaitEvent(c->s_compute2, c->ev_in[0], 0));
+        }
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_free[slot], 0));
         rc = table_dev_impl(c, c->d_in + done, c->d_in + g + done, (long long)n, d_tof, d_kh, rec ? &d : nullptr,
-                            (void *)c->s_compute, sh, 1);
+                            (void *)cs, sh, 1);
         if (rc != TOFRT_OK) break;
-        CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->s_compute));
+        CUDA_TRY(cudaEventRecord(c->ev_done[slot], cs));
         CUDA_TRY(cudaStreamWaitEvent(c->s_copy, c->ev_done[slot], 0));
         auto back = [&](void *dst, const void *src, size_t bytes) {
             return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->s_copy);
@@ -710,6 +758,8 @@ int tofrt_table_host(tofrt_ctx *c, const double *radius, const double *offset, l
         CUDA_TRY(cudaEventRecord(c->ev_free[slot], c->s_copy));
     }
     cudaError_t e1 = cudaStreamSynchronize(c->s_compute), e2 = cudaStreamSynchronize(c->s_copy);
+    cudaError_t e3 = cudaStreamSynchronize(c->s_compute2), e4 = cudaStreamSynchronize(c->s_h2d);
+    if (e1 == cudaSuccess) e1 = e3 != cudaSuccess ? e3 : e4;
     if (rc != TOFRT_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess)
         return fail(TOFRT_E_CUDA, std::string("tofrt_table_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -885,14 +935,7 @@ int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, lo
     const int cap = kHitSlotCap;
     const size_t chunk = std::min<size_t>(g, kHitChunkRows);
     const size_t n_chunks = (g + chunk - 1) / chunk;
-    if (!c->s_compute) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
-        }
-    }
+    { int rcs = ensure_streams(c); if (rcs != TOFRT_OK) return rcs; }
     // grow-only workspace: geometries, and per pipeline slot the row slots, counts, offsets, scan scratch, list, total
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (long long *)nullptr, (long long *)nullptr, (int)(chunk + 1)));
@@ -917,8 +960,6 @@ int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, lo
     }
     if (!c->he_total) CUDA_TRY(cudaHostAlloc((void **)&c->he_total, 4 * sizeof(long long), cudaHostAllocDefault));
     if (!c->ev_cnt[0]) for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_cnt[i], cudaEventDisableTiming));
-    CUDA_TRY(cudaMemcpyAsync(c->he_in, radius, sizeof(double) * g, cudaMemcpyHostToDevice, c->s_compute));
-    CUDA_TRY(cudaMemcpyAsync(c->he_in + g, offset, sizeof(double) * g, cudaMemcpyHostToDevice, c->s_compute));
 
     long long total = 0;
     bool overflow = false;
@@ -948,30 +989,43 @@ int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, lo
         const int slot = (int)(i & 1);
         const int sh = (int)(i / n_chunks);
         const size_t done = (i % n_chunks) * chunk, n = std::min(chunk, g - done);
-        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_free[slot], 0));
+        cudaStream_t cs = slot ? c->s_compute2 : c->s_compute;
+        if (sh == 0) {  // this chunk's geometries (every shooter reuses them)
+            CUDA_TRY(cudaMemcpyAsync(c->he_in + done, radius + done, sizeof(double) * n, cudaMemcpyHostToDevice, c->s_h2d));
+            CUDA_TRY(cudaMemcpyAsync(c->he_in + g + done, offset + done, sizeof(double) * n, cudaMemcpyHostToDevice, c->s_h2d));
+            CUDA_TRY(cudaEventRecord(c->ev_in[slot], c->s_h2d));
+            CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_in[slot], 0));
+        } else if (done == 0) {  // next shooter: both compute streams must have seen every geometry copy
+            CUDA_TRY(cudaEventRecord(c->ev_in[0], c->s_h2d));
+            CUDA_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_in[0], 0));
+            CUDA_TRY(cudaStreamWaitEvent(c->s_compute2, c->ev_in[0], 0));
+        }
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_free[slot], 0));
         HitEmit em;
         em.slots = c->he_slots[slot]; em.count = c->he_cnt[slot]; em.cap = cap;
         rc = table_dev_impl(c, c->he_in + done, c->he_in + g + done, (long long)n, nullptr, nullptr, nullptr,
-                            (void *)c->s_compute, sh, 1, nullptr, nullptr, &em);
+                            (void *)cs, sh, 1, nullptr, nullptr, &em);
         if (rc != TOFRT_OK) break;
         char *L = (char *)c->he_list[slot];
         const int blocks = (int)((n * 32 + 255) / 256);
-        CUDA_TRY(cudaMemsetAsync(c->he_flag[slot], 0, sizeof(int), c->s_compute));
-        tofrt_widen_counts_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, c->s_compute>>>(c->he_cnt[slot], (long long)n, c->he_cnt64[slot]);
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->he_tmp[slot], tmp_bytes, c->he_cnt64[slot], c->he_off[slot], (int)n + 1, c->s_compute));
-        tofrt_gather_slots_kernel<<<blocks, 256, 0, c->s_compute>>>(
+        CUDA_TRY(cudaMemsetAsync(c->he_flag[slot], 0, sizeof(int), cs));
+        tofrt_widen_counts_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, cs>>>(c->he_cnt[slot], (long long)n, c->he_cnt64[slot]);
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->he_tmp[slot], tmp_bytes, c->he_cnt64[slot], c->he_off[slot], (int)n + 1, cs));
+        tofrt_gather_slots_kernel<<<blocks, 256, 0, cs>>>(
             c->he_slots[slot], c->he_cnt[slot], c->he_off[slot], (long long)n, cap, (long long)((size_t)sh * g + done), 0,
             (long long)list_cap, (int *)L, (int *)(L + 4 * list_cap), (int *)(L + 8 * list_cap),
             (double *)(L + 12 * list_cap), c->he_flag[slot]);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(c->ev_done[slot], c->s_compute));
-        CUDA_TRY(cudaMemcpyAsync(&c->he_total[2 * slot], c->he_off[slot] + n, sizeof(long long), cudaMemcpyDeviceToHost, c->s_compute));
-        CUDA_TRY(cudaMemcpyAsync(&c->he_total[2 * slot + 1], c->he_flag[slot], sizeof(int), cudaMemcpyDeviceToHost, c->s_compute));
-        CUDA_TRY(cudaEventRecord(c->ev_cnt[slot], c->s_compute));
+        CUDA_TRY(cudaEventRecord(c->ev_done[slot], cs));
+        CUDA_TRY(cudaMemcpyAsync(&c->he_total[2 * slot], c->he_off[slot] + n, sizeof(long long), cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(&c->he_total[2 * slot + 1], c->he_flag[slot], sizeof(int), cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaEventRecord(c->ev_cnt[slot], cs));
         if (i >= 1) rc = drain(i - 1);   // chunk i is queued: now place chunk i-1's copies
     }
     if (rc == TOFRT_OK && !overflow && n_items >= 1) rc = drain(n_items - 1);
     cudaError_t e1 = cudaStreamSynchronize(c->s_compute), e2 = cudaStreamSynchronize(c->s_copy);
+    cudaError_t e3 = cudaStreamSynchronize(c->s_compute2), e4 = cudaStreamSynchronize(c->s_h2d);
+    if (e1 == cudaSuccess) e1 = e3 != cudaSuccess ? e3 : e4;
     if (rc != TOFRT_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess)
         return fail(TOFRT_E_CUDA, std::string("tofrt_hits_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -1126,14 +1180,7 @@ int tofrt_fermat3d_host(tofrt_ctx *c, const double *fx, const double *fy, const 
     const size_t per_voxel = E3 * (sizeof(double) + (kmin ? sizeof(int) : 0) + (ab ? 2 * sizeof(double) : 0));
     size_t chunk = std::max<size_t>(256, (((size_t)TOFRT_CHUNK_MB << 20) / per_voxel) / 256 * 256);
     chunk = std::min(chunk, n);
-    if (!c->s_compute) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
-        }
-    }
+    { int rcs = ensure_streams(c); if (rcs != TOFRT_OK) return rcs; }
     double *d_f = nullptr;
     char *slot[2] = {nullptr, nullptr};
     const size_t slot_bytes = chunk * per_voxel + 3 * 256;

@@ -85,7 +85,12 @@ __device__ __forceinline__ void chord_intersection(const double2 *lens, const do
 // (Measured and rejected: lane l walking the CONSECUTIVE rays l C .. l C + C-1, which predicts the next bracket to
 // +-1 sample from the lane's own previous ray -- the search gets cheaper, but scattered shared-memory probes, the
 // slow paths of the 4 % dead rays now present in every warp and a 2x slower literal scan cost more: 29.8 vs 25.2 ms.)
-template <bool HG, bool GUIDED, bool FLAT, bool VEC, bool STATS>
+//
+// SPLIT (small-G latency mode): a whole CTA owns one (shooter, geometry) at a time and its warps take one 32-ray
+// chunk each (requires ceil(K / 32) <= warps per CTA; warps beyond the last chunk repeat it, which is idempotent),
+// with a CTA-wide first-hit reduction in shared memory.  With fewer geometries than resident warps -- the
+// reference's own 210-geometry sweep -- this turns 29 serial chunks per warp into one: 0.23 ms -> tens of us.
+template <bool HG, bool GUIDED, bool FLAT, bool VEC, bool STATS, bool SPLIT = false>
 __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_BLOCKS)
     tofrt_table_kernel(DevSetup S, TableArgs T)
 {
@@ -125,8 +130,8 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
     // atomicMin below happens in L2 and must not be shadowed by a stale L1 line
     typedef typename std::conditional<HG, volatile double, double>::type tof_t;
     typedef typename std::conditional<HG, volatile int, int>::type khit_t;
-    tof_t *w_tof = s_tof + (size_t)warp * E;
-    khit_t *w_khit = s_khit + (size_t)warp * E;
+    tof_t *w_tof = s_tof + (SPLIT ? (size_t)0 : (size_t)warp * E);
+    khit_t *w_khit = s_khit + (SPLIT ? (size_t)0 : (size_t)warp * E);
     const int C = S.C;               // 32-ray chunks per shot
     const unsigned FULL = 0xffffffffu;
     tofrt_vec_lens VL = S.VL;  // lens constants of the vector form (uniform)
@@ -147,10 +152,10 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
     const unsigned long long total = (unsigned long long)T.G * (unsigned long long)T.s_count;
     for (;;) {
         __syncthreads();  // everyone has read the previous s_base
-        if (threadIdx.x == 0) s_base = atomicAdd(T.counter, (unsigned long long)kWarps);
+        if (threadIdx.x == 0) s_base = atomicAdd(T.counter, (unsigned long long)(SPLIT ? 1 : kWarps));
         __syncthreads();
         if (s_base >= total) break;
-        const unsigned long long g64 = s_base + warp;
+        const unsigned long long g64 = s_base + (SPLIT ? 0 : warp);
         if (g64 >= total) continue;  // tail: fewer items than warps
         const long long w = (long long)g64;               // work item = (shooter, geometry)
         long long g = w, s_local = 0;
@@ -160,11 +165,11 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
         const double r_outer = T.radius[g], pipe_offset = T.offset[g];
         const double rsq = r_outer * r_outer, offsq = pipe_offset * pipe_offset, rsq2 = rsq * rsq;
         if (HG) { w_tof = T.tof + (size_t)w * E; w_khit = T.k_hit + (size_t)w * E; }
-        for (int e = lane; e < E; e += 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0; }
-        __syncwarp();
+        for (int e = SPLIT ? (int)threadIdx.x : lane; e < E; e += SPLIT ? kThreads : 32) { w_khit[e] = kNoHit; w_tof[e] = 0.0; }
+        if (SPLIT) __syncthreads(); else __syncwarp();
 
         int h1 = -1, h2 = -1;  // guided search: this lane's bracket starts in the previous two chunks
-        for (int c = 0; c < C; ++c) {
+        for (int c = SPLIT ? min(warp, C - 1) : 0; c < C; c += SPLIT ? C : 1) {
             const int k = min((c << 5) + lane, K - 1);
             // per-ray constants of the shot: one coalesced, L1-resident load per 32 rays
             const double *rt = ray_t + c * (kRayPlanes * 32);
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
             bool special = false;
             if (S.has_nonfinite_rx) special = isinf(target_x);  // uniform: no receiver is infinite in practice
             const bool want_legs = T.rec.legs != nullptr;
-            if (__any_sync(FULL, hi > lo || special || want_legs)) {
+            if (SPLIT || __any_sync(FULL, hi > lo || special || want_legs)) {  // (SPLIT: a CTA barrier sits inside)
                 bool mine = false;
                 // np.isclose(target_x, x_e): |target_x - x_e| <= atol + rtol |x_e| for a finite x_e (the sorted copy
                 // holds finite receivers only), or equality.  Usually one candidate: straight-line, the rest in a loop.
@@ -496,7 +501,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                     for (int e = 0; e < E; ++e)
                         if (target_x == S.x_rx[e]) { atomicMin(const_cast<int *>(&w_khit[e]), k); mine = true; }
                 }
-                __syncwarp();
+                if (SPLIT) __syncthreads(); else __syncwarp();  // every atomicMin on this row is in: the winners are known
                 if (mine || want_legs) {
                     // main_rt.py:497-500 / main_compare.py:514-517
                     if (STATS) st[kStWinners] += 1;
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
             }
         }
         // ---- one geometry done: coalesced row of the [G][E] table, or (sparse emission) only its hits ----
-        __syncwarp();
+        if (SPLIT) { __syncthreads(); if (warp != 0) continue; } else __syncwarp();  // (SPLIT: warp 0 stores the CTA's row)
         if (!HG && T.hit_slots) {
             int base = 0;
             uint4 *slot = T.hit_slots + (size_t)w * T.hit_cap;

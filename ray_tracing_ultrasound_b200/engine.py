@@ -122,6 +122,11 @@ class TofEngine:
         _capi.check(self._lib.tofrt_set_option(self._ctx, 3, {"angle": 0, "vector": 1}[mode]))
         return self
 
+    def set_small_g(self, on):
+        """Small-G latency mode (TOFRT_OPT_SMALL_G, default on): few geometries run a CTA per geometry."""
+        _capi.check(self._lib.tofrt_set_option(self._ctx, 5, 1 if on else 0))
+        return self
+
     @property
     def math_mode(self):
         return "vector" if self._lib.tofrt_get_info(self._ctx, 3) == 1 else "angle"

@@ -272,6 +272,43 @@ def test_two_engines_with_different_sizes_on_one_gpu(engine):
     big.close(); small.close()
 
 
+def test_small_g_latency_mode_equals_the_regular_kernel(engine, oracle_dm):
+    """TOFRT_OPT_SMALL_G: a CTA per geometry with one chunk per warp (few geometries) gives the regular kernel's
+    bytes -- table, records, hit list -- on the reference's 210-geometry sweep, a single geometry, several shooters."""
+    x_a, z_a, alpha, zf = _std(engine)
+    radii, offsets = rs.sweep_grid()
+    keys = ("idx", "target_x", "pipe_x", "lens2_z", "legs")
+    engine.set_small_g(False)
+    a = engine.tof_table(radii, offsets, records=keys)
+    one_a = engine.tof_table(radii[57:58], offsets[57:58])
+    hits_a = engine.tof_hits(radii, offsets)
+    engine.set_small_g(True)
+    b = engine.tof_table(radii, offsets, records=keys)
+    one_b = engine.tof_table(radii[57:58], offsets[57:58])
+    hits_b = engine.tof_hits(radii, offsets)
+    assert np.array_equal(a.tof, b.tof) and np.array_equal(a.k_hit, b.k_hit) and int(b.hit.sum()) == 498
+    for k in keys:
+        assert _same(a.records[k], b.records[k]), k
+    assert np.array_equal(one_a.tof, one_b.tof) and np.array_equal(one_a.k_hit, one_b.k_hit)
+    assert all(np.array_equal(u, v) for u, v in zip(hits_a, hits_b)) and len(hits_b[0]) == 498
+    p = oracle_dm.params()
+    tof, k_hit, idx = oracle_dm.table(p, radii, offsets, x_a[32], z_a[32], zf, alpha, x_a, want_idx=True)
+    assert np.array_equal(b.k_hit, k_hit.T) and np.array_equal(b.tof, tof.T) and np.array_equal(b.records["idx"], idx)
+    # several shooters (3 x 20 items), and the K = 1810 case of main_compare.py (57 chunks > 32 warps: regular kernel)
+    engine.setup(alpha, zf, x_a[30:33], z_a[30:33], x_a)
+    engine.set_small_g(False)
+    m0 = engine.tof_table(radii[:20], offsets[:20])
+    engine.set_small_g(True)
+    m1 = engine.tof_table(radii[:20], offsets[:20])
+    assert m1.tof.shape == (3, 20, 65) and np.array_equal(m0.tof, m1.tof) and np.array_equal(m0.k_hit, m1.k_hit)
+    _std(engine, rs.NUM_ALPHA_POINTS_COMPARE)
+    c1 = engine.tof_table(radii[:3], offsets[:3])
+    engine.set_small_g(False)
+    c0 = engine.tof_table(radii[:3], offsets[:3])
+    engine.set_small_g(True)
+    assert np.array_equal(c0.tof, c1.tof) and np.array_equal(c0.k_hit, c1.k_hit)
+
+
 def test_full_size_grid_properties(engine, oracle_dm):
     """BASELINE config 3 at full size (129 receivers, 1024 x 1024 geometries): the table is
     checked through size-independent properties -- a random subsample against the oracle,
