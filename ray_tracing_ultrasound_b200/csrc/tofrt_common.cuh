@@ -24,6 +24,8 @@ constexpr int kThreadsGuided = TOFRT_THREADS_GUIDED;
 #endif
 constexpr int kChunk = TOFRT_SCAN_CHUNK;  // lens samples per early-exit check of the literal scan (<= 32)
 constexpr int kNoHit = 0x7fffffff;
+constexpr int kSplitQueue = 256;  // small-G mode: rays per geometry the CTA-wide on-sample pass can queue
+constexpr size_t kSplitQueueBytes = 16 + (size_t)kSplitQueue * (sizeof(double2) + sizeof(int));
 // per-ray tables of the FP64 table kernel: ray_t[shooter][c][plane][lane] holds ray min(32 c + lane, K-1)
 enum { kPlaneXp, kPlaneZp, kPlaneCpq, kPlaneSpq, kPlaneZf, kPlaneApq, kPlaneBpq, kPlanePhi, kRayPlanes };
 // executed-work counters of the instrumented (STATS) instantiation, per thread-ray (tofrt_last_stats)

@@ -39,7 +39,9 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <atomic>
@@ -104,8 +106,9 @@ table_kernel_t pick_table_kernel(bool hg, bool guided, bool flat, bool vec, bool
 // variables).  The per-function opt-in attribute is per DEVICE, not per context, so it is always raised to this
 // maximum: two live contexts with different K / E on one GPU can then never lower each other's limit.
 constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;
+constexpr int kHitRing = 3;                  // chunk buffers in flight in tofrt_hits_host
 constexpr int kHitSlotCap = 16;              // (e, k, tof) entries per row slot of the fused sparse emission
-constexpr size_t kHitChunkRows = 131072;     // rows per pipelined chunk of tofrt_hits_host (32 MB of slots)
+constexpr size_t kHitChunkRows = 32768;      // rows per pipelined chunk of tofrt_hits_host (8 MB of slots; measured best of 32 Ki .. 1 Mi)
 constexpr unsigned kCounterSlots = 64, kCounterStride = 16;  // 128 B per slot: [0] work counter, [1..] statistics
 
 struct tofrt_ctx {
@@ -157,15 +160,16 @@ struct tofrt_ctx {
     // tofrt_hits_host workspace (grow-only): dense intermediate, counts/offsets, scan scratch, hit list
     void *hw[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t hw_bytes[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    // fused sparse emission (tofrt_hits_host): geometries + two pipeline slots
+    // fused sparse emission (tofrt_hits_host): geometries + a ring of three chunk buffers
     double *he_in = nullptr; size_t he_in_bytes = 0;
-    uint4 *he_slots[2] = {nullptr, nullptr};
-    int *he_cnt[2] = {nullptr, nullptr}, *he_flag[2] = {nullptr, nullptr};
-    long long *he_cnt64[2] = {nullptr, nullptr}, *he_off[2] = {nullptr, nullptr};
-    void *he_tmp[2] = {nullptr, nullptr}, *he_list[2] = {nullptr, nullptr};
-    size_t he_bytes[2][7] = {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
-    long long *he_total = nullptr;   // pinned: per slot (hits in the chunk, overflow flag)
-    cudaEvent_t ev_cnt[2] = {nullptr, nullptr};
+    uint4 *he_slots[kHitRing] = {};
+    int *he_cnt[kHitRing] = {}, *he_flag[kHitRing] = {};
+    long long *he_cnt64[kHitRing] = {}, *he_off[kHitRing] = {};
+    void *he_tmp[kHitRing] = {}, *he_list[kHitRing] = {};
+    size_t he_bytes[kHitRing][7] = {};
+    long long *he_total = nullptr;   // pinned: per ring entry (hits in the chunk, overflow flag)
+    cudaStream_t s_post = nullptr;   // high priority: the chunks' scan + gather
+    cudaEvent_t ev_k[kHitRing] = {}, ev_post[kHitRing] = {}, ev_cnt[kHitRing] = {}, ev_out[kHitRing] = {};
     double *d_d1 = nullptr;   // Fermat solver: |A_e - P_j|/c1, built lazily per setup
     // 3-D two-point solve (tofrt_fermat3d_setup)
     bool f3_ready = false;
@@ -226,11 +230,12 @@ int tofrt_destroy(tofrt_ctx *c)
     cudaFree(c->f3_geo); cudaFree(c->f3_smp);
     for (int i = 0; i < 10; ++i) cudaFree(c->hw[i]);
     cudaFree(c->he_in);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kHitRing; ++i) {
         cudaFree(c->he_slots[i]); cudaFree(c->he_cnt[i]); cudaFree(c->he_flag[i]); cudaFree(c->he_cnt64[i]);
         cudaFree(c->he_off[i]); cudaFree(c->he_tmp[i]); cudaFree(c->he_list[i]);
-        if (c->ev_cnt[i]) cudaEventDestroy(c->ev_cnt[i]);
+        for (cudaEvent_t e : {c->ev_k[i], c->ev_post[i], c->ev_cnt[i], c->ev_out[i]}) if (e) cudaEventDestroy(e);
     }
+    if (c->s_post) cudaStreamDestroy(c->s_post);
     if (c->he_total) cudaFreeHost(c->he_total);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -600,11 +605,13 @@ static int table_dev_impl(tofrt_ctx *c, const double *d_radius, const double *d_
     // leaves most of the machine idle while each warp walks its 29 chunks one after the other; a CTA per item with a
     // chunk per warp finishes an item in the time of ONE chunk.  (Test hook and instrumented runs keep the main kernel.)
     const bool split = guided && !c->S.hits_in_global && !c->opt_stats && !inject_m && c->opt_small_g &&
-                       c->S.C <= kThreadsGuided / 32 && warps_needed < (long long)c->sm_count * c->ctas_per_sm * wpc / 2;
+                       c->S.C <= kThreadsGuided / 32 && warps_needed < (long long)c->sm_count * c->ctas_per_sm * wpc / 2 &&
+                       smem + kSplitQueueBytes <= kMaxDynSmem;
     if (split) {
         grid = (int)std::min<long long>((long long)c->sm_count * c->ctas_per_sm, warps_needed);
-        if (c->S.vector_math) tofrt_table_kernel<false, true, false, true, false, true><<<grid, threads, smem, st>>>(c->S, T);
-        else tofrt_table_kernel<false, true, false, false, false, true><<<grid, threads, smem, st>>>(c->S, T);
+        const size_t smem_split = smem + kSplitQueueBytes;
+        if (c->S.vector_math) tofrt_table_kernel<false, true, false, true, false, true><<<grid, threads, smem_split, st>>>(c->S, T);
+        else tofrt_table_kernel<false, true, false, false, false, true><<<grid, threads, smem_split, st>>>(c->S, T);
         CUDA_TRY(cudaGetLastError());
         return TOFRT_OK;
     }
@@ -917,8 +924,15 @@ static int hits_host_dense(tofrt_ctx *c, const double *radius, const double *off
 }
 
 // Hit list through the fused emission: the table kernel writes each row's hits into a small per-row slot (no dense
-// table is stored or re-read); per chunk of rows a scan of the counts and an ordered gather build the list, and the
-// list of chunk i travels to the host while chunk i+1 is traced (two slots, two streams, as tofrt_table_host).
+// table is stored or re-read); per chunk of rows a scan of the counts and an ordered gather ("post") build the list,
+// which travels to the host while later chunks are traced.
+//
+// Streams.  The table kernel is persistent and fills every SM (1024 threads x 64 registers), so nothing else runs
+// beside it: chunk i's post kernels only get SMs when the NEXT table kernel runs out of work.  If they sat in front of
+// chunk i+2's kernel on the same stream, the GPU would drain at every chunk boundary (measured: +0.9 ms per 1 Mi
+// rows).  So the table kernels alternate between two streams and never wait for a post; the posts go to a third,
+// HIGH-PRIORITY stream (their blocks win the SMs a finishing table kernel frees, ahead of the next kernel's CTAs), and
+// everything they touch is a ring of three buffers: chunk i+3 reuses what chunk i's copy to the host has released.
 int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, long long G, long long capacity,
                     int *hit_g, int *hit_e, int *hit_k, double *hit_tof, long long *n_hits)
 {
@@ -933,10 +947,27 @@ int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, lo
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t g = (size_t)G, NSH = (size_t)c->n_shooters;
     const int cap = kHitSlotCap;
-    const size_t chunk = std::min<size_t>(g, kHitChunkRows);
+    size_t chunk_rows = kHitChunkRows;
+    if (const char *env = getenv("TOFRT_HIT_CHUNK_ROWS")) {  // tuning knob
+        const long long v = atoll(env);
+        if (v >= 1024) chunk_rows = (size_t)v;
+    }
+    const size_t chunk = std::min<size_t>(g, chunk_rows);
     const size_t n_chunks = (g + chunk - 1) / chunk;
     { int rcs = ensure_streams(c); if (rcs != TOFRT_OK) return rcs; }
-    // grow-only workspace: geometries, and per pipeline slot the row slots, counts, offsets, scan scratch, list, total
+    if (!c->s_post) {
+        int lo_p = 0, hi_p = 0;  // (numerically lowest = highest priority)
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->s_post, cudaStreamNonBlocking, hi_p));
+        for (int i = 0; i < kHitRing; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_post[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_cnt[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaHostAlloc((void **)&c->he_total, 2 * kHitRing * sizeof(long long), cudaHostAllocDefault));
+    }
+    // grow-only workspace: geometries, and per ring entry the row slots, counts, offsets, scan scratch, list, flag
     size_t tmp_bytes = 0;
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (long long *)nullptr, (long long *)nullptr, (int)(chunk + 1)));
     auto grow = [&](void **q, size_t *have, size_t bytes) {
@@ -949,7 +980,7 @@ int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, lo
     };
     const size_t list_cap = chunk * (size_t)cap;  // most hits one chunk can deliver through the slots
     CUDA_TRY(grow((void **)&c->he_in, &c->he_in_bytes, sizeof(double) * 2 * g));
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kHitRing; ++s) {
         CUDA_TRY(grow((void **)&c->he_slots[s], &c->he_bytes[s][0], sizeof(uint4) * list_cap));
         CUDA_TRY(grow((void **)&c->he_cnt[s], &c->he_bytes[s][1], sizeof(int) * chunk));
         CUDA_TRY(grow((void **)&c->he_cnt64[s], &c->he_bytes[s][2], sizeof(long long) * (chunk + 1)));
@@ -958,8 +989,6 @@ int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, lo
         CUDA_TRY(grow((void **)&c->he_list[s], &c->he_bytes[s][5], list_cap * 20));
         CUDA_TRY(grow((void **)&c->he_flag[s], &c->he_bytes[s][6], sizeof(int)));
     }
-    if (!c->he_total) CUDA_TRY(cudaHostAlloc((void **)&c->he_total, 4 * sizeof(long long), cudaHostAllocDefault));
-    if (!c->ev_cnt[0]) for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_cnt[i], cudaEventDisableTiming));
 
     long long total = 0;
     bool overflow = false;
@@ -967,30 +996,32 @@ int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, lo
     const size_t n_items = n_chunks * NSH;
     // drain(i): the host learns chunk i's hit count, then queues its copies at the running offset
     auto drain = [&](size_t i) -> int {
-        const int slot = (int)(i & 1);
-        CUDA_TRY(cudaEventSynchronize(c->ev_cnt[slot]));
-        const long long got = c->he_total[2 * slot];
-        if (c->he_total[2 * slot + 1]) overflow = true;
+        const int b = (int)(i % kHitRing);
+        CUDA_TRY(cudaEventSynchronize(c->ev_cnt[b]));
+        const long long got = c->he_total[2 * b];
+        if (c->he_total[2 * b + 1]) overflow = true;
         const long long room = std::max<long long>(0, capacity - total);
         const size_t n = (size_t)std::min<long long>(got, room);
         if (n && !overflow) {
-            const char *L = (const char *)c->he_list[slot];
-            CUDA_TRY(cudaStreamWaitEvent(c->s_copy, c->ev_done[slot], 0));
+            const char *L = (const char *)c->he_list[b];
+            CUDA_TRY(cudaStreamWaitEvent(c->s_copy, c->ev_post[b], 0));
             CUDA_TRY(cudaMemcpyAsync(hit_g + total, L, sizeof(int) * n, cudaMemcpyDeviceToHost, c->s_copy));
             CUDA_TRY(cudaMemcpyAsync(hit_e + total, L + 4 * list_cap, sizeof(int) * n, cudaMemcpyDeviceToHost, c->s_copy));
             CUDA_TRY(cudaMemcpyAsync(hit_k + total, L + 8 * list_cap, sizeof(int) * n, cudaMemcpyDeviceToHost, c->s_copy));
             CUDA_TRY(cudaMemcpyAsync(hit_tof + total, L + 12 * list_cap, sizeof(double) * n, cudaMemcpyDeviceToHost, c->s_copy));
         }
-        CUDA_TRY(cudaEventRecord(c->ev_free[slot], c->s_copy));
+        CUDA_TRY(cudaEventRecord(c->ev_out[b], c->s_copy));
         total += got;
         return TOFRT_OK;
     };
+    size_t drained = 0;
     for (size_t i = 0; i < n_items && rc == TOFRT_OK && !overflow; ++i) {
-        const int slot = (int)(i & 1);
+        const int b = (int)(i % kHitRing);
         const int sh = (int)(i / n_chunks);
         const size_t done = (i % n_chunks) * chunk, n = std::min(chunk, g - done);
-        cudaStream_t cs = slot ? c->s_compute2 : c->s_compute;
+        cudaStream_t cs = (i & 1) ? c->s_compute2 : c->s_compute;
         if (sh == 0) {  // this chunk's geometries (every shooter reuses them)
+            const int slot = (int)(i & 1);
             CUDA_TRY(cudaMemcpyAsync(c->he_in + done, radius + done, sizeof(double) * n, cudaMemcpyHostToDevice, c->s_h2d));
             CUDA_TRY(cudaMemcpyAsync(c->he_in + g + done, offset + done, sizeof(double) * n, cudaMemcpyHostToDevice, c->s_h2d));
             CUDA_TRY(cudaEventRecord(c->ev_in[slot], c->s_h2d));
@@ -1000,32 +1031,38 @@ int tofrt_hits_host(tofrt_ctx *c, const double *radius, const double *offset, lo
             CUDA_TRY(cudaStreamWaitEvent(c->s_compute, c->ev_in[0], 0));
             CUDA_TRY(cudaStreamWaitEvent(c->s_compute2, c->ev_in[0], 0));
         }
-        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_free[slot], 0));
+        if (i >= (size_t)kHitRing) CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_out[b], 0));  // ring entry released by chunk i-3's copy
         HitEmit em;
-        em.slots = c->he_slots[slot]; em.count = c->he_cnt[slot]; em.cap = cap;
+        em.slots = c->he_slots[b]; em.count = c->he_cnt[b]; em.cap = cap;
         rc = table_dev_impl(c, c->he_in + done, c->he_in + g + done, (long long)n, nullptr, nullptr, nullptr,
                             (void *)cs, sh, 1, nullptr, nullptr, &em);
         if (rc != TOFRT_OK) break;
-        char *L = (char *)c->he_list[slot];
+        CUDA_TRY(cudaEventRecord(c->ev_k[b], cs));
+        // post (high priority): counts -> offsets -> ordered list of this chunk
+        cudaStream_t ps = c->s_post;
+        char *L = (char *)c->he_list[b];
         const int blocks = (int)((n * 32 + 255) / 256);
-        CUDA_TRY(cudaMemsetAsync(c->he_flag[slot], 0, sizeof(int), cs));
-        tofrt_widen_counts_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, cs>>>(c->he_cnt[slot], (long long)n, c->he_cnt64[slot]);
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->he_tmp[slot], tmp_bytes, c->he_cnt64[slot], c->he_off[slot], (int)n + 1, cs));
-        tofrt_gather_slots_kernel<<<blocks, 256, 0, cs>>>(
-            c->he_slots[slot], c->he_cnt[slot], c->he_off[slot], (long long)n, cap, (long long)((size_t)sh * g + done), 0,
+        CUDA_TRY(cudaStreamWaitEvent(ps, c->ev_k[b], 0));
+        CUDA_TRY(cudaMemsetAsync(c->he_flag[b], 0, sizeof(int), ps));
+        tofrt_widen_counts_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ps>>>(c->he_cnt[b], (long long)n, c->he_cnt64[b]);
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(c->he_tmp[b], tmp_bytes, c->he_cnt64[b], c->he_off[b], (int)n + 1, ps));
+        tofrt_gather_slots_kernel<<<blocks, 256, 0, ps>>>(
+            c->he_slots[b], c->he_cnt[b], c->he_off[b], (long long)n, cap, (long long)((size_t)sh * g + done), 0,
             (long long)list_cap, (int *)L, (int *)(L + 4 * list_cap), (int *)(L + 8 * list_cap),
-            (double *)(L + 12 * list_cap), c->he_flag[slot]);
+            (double *)(L + 12 * list_cap), c->he_flag[b]);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(c->ev_done[slot], cs));
-        CUDA_TRY(cudaMemcpyAsync(&c->he_total[2 * slot], c->he_off[slot] + n, sizeof(long long), cudaMemcpyDeviceToHost, cs));
-        CUDA_TRY(cudaMemcpyAsync(&c->he_total[2 * slot + 1], c->he_flag[slot], sizeof(int), cudaMemcpyDeviceToHost, cs));
-        CUDA_TRY(cudaEventRecord(c->ev_cnt[slot], cs));
-        if (i >= 1) rc = drain(i - 1);   // chunk i is queued: now place chunk i-1's copies
+        CUDA_TRY(cudaEventRecord(c->ev_post[b], ps));
+        CUDA_TRY(cudaMemcpyAsync(&c->he_total[2 * b], c->he_off[b] + n, sizeof(long long), cudaMemcpyDeviceToHost, ps));
+        CUDA_TRY(cudaMemcpyAsync(&c->he_total[2 * b + 1], c->he_flag[b], sizeof(int), cudaMemcpyDeviceToHost, ps));
+        CUDA_TRY(cudaEventRecord(c->ev_cnt[b], ps));
+        // chunk i's post runs when chunk i+1's kernel ends: the host stays two chunks ahead of the counts it waits for
+        if (i >= 2) { rc = drain(i - 2); drained = i - 1; }
     }
-    if (rc == TOFRT_OK && !overflow && n_items >= 1) rc = drain(n_items - 1);
+    for (; rc == TOFRT_OK && !overflow && drained < n_items; ++drained) rc = drain(drained);
     cudaError_t e1 = cudaStreamSynchronize(c->s_compute), e2 = cudaStreamSynchronize(c->s_copy);
     cudaError_t e3 = cudaStreamSynchronize(c->s_compute2), e4 = cudaStreamSynchronize(c->s_h2d);
-    if (e1 == cudaSuccess) e1 = e3 != cudaSuccess ? e3 : e4;
+    cudaError_t e5 = cudaStreamSynchronize(c->s_post);
+    if (e1 == cudaSuccess) e1 = e3 != cudaSuccess ? e3 : (e4 != cudaSuccess ? e4 : e5);
     if (rc != TOFRT_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess)
         return fail(TOFRT_E_CUDA, std::string("tofrt_hits_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));

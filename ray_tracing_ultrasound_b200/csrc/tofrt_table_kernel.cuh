@@ -4,7 +4,7 @@
 
 // ---- exact (slow) pieces of find_line_curve_intersection ------------------------
 
-// first j in [j0, N-2] with a sign-class change between samples j and j+1, else -1
+// first j in [j0, N-2] with a sign-class change between samples j and j+1, else -1 (one thread, one ray)
 __device__ __noinline__ int scan_exact_from(const double2 *lens, int N, double m, double b, int j0)
 {
     int cprev = sign_class(line_diff(lens[j0], m, b));
@@ -12,6 +12,24 @@ __device__ __noinline__ int scan_exact_from(const double2 *lens, int N, double m
         int cnext = sign_class(line_diff(lens[j + 1], m, b));
         if (class_change(cprev, cnext)) return j;
         cprev = cnext;
+    }
+    return -1;
+}
+
+// The reference's scan, exactly (np.sign classes incl. zero and NaN): first j in [j0, N-2] with a class change between
+// samples j and j+1, else -1 -- for ONE line, evaluated by the whole warp (32 sample pairs per step).  The rare rays
+// no cheaper argument decides come here one after the other in the small-G mode, where a per-thread loop over up to N
+// samples (scan_exact_from: 900 dependent iterations, ~45 us) would be the critical path of the whole call; in the
+// throughput kernel such a ray is one slow warp among thousands and the per-thread loop keeps the hot stream leaner
+// (measured: the cooperative form there costs 1.5 %).
+__device__ __noinline__ int warp_scan_exact(const double2 *lens, int N, double m, double b, int j0, int lane)
+{
+    for (int base = j0; base + 1 < N; base += 32) {
+        const int j = base + lane;
+        bool chg = false;
+        if (j + 1 < N) chg = class_change(sign_class(line_diff(lens[j], m, b)), sign_class(line_diff(lens[j + 1], m, b)));
+        const unsigned mask = __ballot_sync(0xffffffffu, chg);
+        if (mask) return base + __ffs(mask) - 1;
     }
     return -1;
 }
@@ -106,6 +124,9 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
     int *s_perm = reinterpret_cast<int *>(s_tof + (HG ? (size_t)0 : (size_t)kWarps * E));
     int *s_khit = s_perm + S.E_sorted;               // [kWarps][E] (absent when HG)
     int *s_bucket = s_khit + (HG ? (size_t)0 : (size_t)kWarps * E);  // [nb] packed (first, count)
+    // small-G mode: queue of rays for the CTA-wide on-sample pass (kSplitQueue lines + results, after the cell table)
+    double2 *s_qmb = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(s_bucket + S.nb) + 15) & ~(uintptr_t)15);
+    int *s_qres = reinterpret_cast<int *>(s_qmb + kSplitQueue);
 
     // Stage the sampled surface once per CTA: two TMA bulk copies (lens samples, chords; 16-byte
     // aligned, multiples of 16 bytes) complete on one mbarrier while the threads load the small
@@ -213,6 +234,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
             // fast path precondition: every diff is finite, so only {-,0,+} occur
             const bool fast = S.tables_ok && fabs(m) < 1e150 && fabs(b) < 1e150;
             int idx = -1;             // >= 0 segment, -1 none
+            int scan_from = -1;       // >= 0: this ray still needs the reference's exact scan from that sample on
             bool need_scan = fast;    // lanes whose index the O(N) scan below still has to find
             bool skip_on_sample = false;
             if (GUIDED) {
@@ -323,7 +345,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                     if (STATS) st[kStDiffs] += 1;
                     const bool same = d0 > 0.0 ? dn > 0.0 : dn < 0.0;
                     if (!same) idx = lo;
-                    else if (lo + 2 < N) idx = scan_exact_from(s_lens, N, m, b, lo + 1);
+                    else if (lo + 2 < N) { if (SPLIT) scan_from = lo + 1; else idx = scan_exact_from(s_lens, N, m, b, lo + 1); }
                     need_scan = false;  // no change after lo either => none at all (on-sample test decides)
                 } else if (certain_none) {
                     need_scan = false;
@@ -335,7 +357,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
             if (STATS) { st[kStRays] += 1; st[kStScan] += need_scan; }
             if (GUIDED) {
                 // a ray the guided search could not decide (|diff| <= tol where it matters): plain exact scan
-                if (need_scan) { idx = scan_exact_from(s_lens, N, m, b, 0); flagged = 0; }
+                if (need_scan) { if (SPLIT) scan_from = 0; else idx = scan_exact_from(s_lens, N, m, b, 0); flagged = 0; }
             } else if (__any_sync(FULL, need_scan)) {
                 unsigned hp = hi32(line_diff(s_lens[0], m, b));
                 for (int base = 1; base < Npad; base += kChunk) {
@@ -377,11 +399,22 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 if (!fast) {
                     // a NaN line makes every diff NaN: np.sign changes "between" samples 0 and 1 (main_rt.py:82)
                     if (m != m || b != b) idx = 0;
+                    else if (SPLIT) scan_from = 0;
                     else idx = scan_exact_from(s_lens, N, m, b, 0);
                 }
                 // conservative flag without a real change (a denormal diff): keep going exactly
                 else if (!GUIDED && need_scan && flagged >= 0 && flagged + kChunk - 1 < N - 1)
                     idx = scan_exact_from(s_lens, N, m, b, flagged + kChunk - 1);
+            }
+            if (SPLIT) {  // the exact scans, one ray at a time, 32 sample pairs per step (see warp_scan_exact)
+                unsigned need = __ballot_sync(FULL, scan_from >= 0);
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int r = warp_scan_exact(s_lens, N, __shfl_sync(FULL, m, src), __shfl_sync(FULL, b, src),
+                                                  __shfl_sync(FULL, scan_from, src), lane);
+                    if (lane == src) idx = r;
+                }
             }
             // ---- main_rt.py:84-96 no crossing: is a sample on the line (|diff| <= 1e-8)? ----
             // All diffs of such a ray have one sign, so the unsigned minimum of their high words is
@@ -394,6 +427,34 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                               (gmin & 0x7fffffffu) <= 0x3e45798eu /* hi32(1e-8) */);
                 unsigned need = __ballot_sync(FULL, maybe);
                 if (STATS) st[kStOnSample] += maybe;
+                if (SPLIT) {
+                    // Small-G mode: the rays of one geometry that need this pass usually sit in one or two chunks (the
+                    // ones grazing the lens apex), i.e. in one or two warps, while the other ~30 warps of the CTA would
+                    // wait at the next barrier: queue them and let every warp take one ray at a time.
+                    __shared__ int s_qn;
+                    if (threadIdx.x == 0) s_qn = 0;
+                    __syncthreads();
+                    int myq = -1;
+                    if (maybe) {
+                        myq = atomicAdd(&s_qn, 1);
+                        if (myq < kSplitQueue) s_qmb[myq] = make_double2(m, b);
+                    }
+                    need = __ballot_sync(FULL, maybe && myq >= kSplitQueue);   // overflow: the per-warp path below
+                    __syncthreads();
+                    const int nq = min(s_qn, kSplitQueue);
+                    for (int q = warp; q < nq; q += kWarps) {
+                        const double2 mb = s_qmb[q];
+                        int first = kNoHit;
+                        for (int j = lane; j < N; j += 32) {
+                            double dd = line_diff(s_lens[j], mb.x, mb.y);
+                            if (fabs(dd) <= 1e-8) { first = j; break; }
+                        }
+                        first = __reduce_min_sync(FULL, first);
+                        if (lane == 0) s_qres[q] = first;
+                    }
+                    __syncthreads();
+                    if (myq >= 0 && myq < kSplitQueue && s_qres[myq] != kNoHit) on_sample = s_qres[myq];
+                }
                 while (need) {
                     int src = __ffs(need) - 1;
                     need &= need - 1;
