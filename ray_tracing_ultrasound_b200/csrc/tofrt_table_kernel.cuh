@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
     khit_t *w_khit = s_khit + (SPLIT ? (size_t)0 : (size_t)warp * E);
     const int C = S.C;               // 32-ray chunks per shot
     const unsigned FULL = 0xffffffffu;
+    const bool rare_path = S.has_nonfinite_rx != 0 || T.rec.legs != nullptr;
     tofrt_vec_lens VL = S.VL;  // lens constants of the vector form (uniform)
     VL.flat = FLAT ? 1 : 0;
     // executed-work counters (STATS only): rays, rays with a bracket, cond probes, exact diffs, rays that entered
@@ -542,10 +543,12 @@ __global__ void __launch_bounds__(GUIDED ? kThreadsGuided : kThreads, TOFRT_MIN_
                 hi = lo;
                 while (hi < S.E_sorted && s_xs[hi] <= th) ++hi;
             }
-            bool special = false;
-            if (S.has_nonfinite_rx) special = isinf(target_x);  // uniform: no receiver is infinite in practice
-            const bool want_legs = T.rec.legs != nullptr;
-            if (SPLIT || __any_sync(FULL, hi > lo || special || want_legs)) {  // (SPLIT: a CTA barrier sits inside)
+            bool special = false, want_legs = false;
+            if (rare_path) {  // uniform: infinite receivers or the per-ray leg records -- neither in a production table call
+                special = S.has_nonfinite_rx && isinf(target_x);
+                want_legs = T.rec.legs != nullptr;
+            }
+            if (SPLIT || rare_path || __any_sync(FULL, hi > lo)) {  // (SPLIT: a CTA barrier sits inside)
                 bool mine = false;
                 // np.isclose(target_x, x_e): |target_x - x_e| <= atol + rtol |x_e| for a finite x_e (the sorted copy
                 // holds finite receivers only), or equality.  Usually one candidate: straight-line, the rest in a loop.

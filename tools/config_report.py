@@ -16,8 +16,8 @@ def timed(fn, reps=3):
     return out, e0.elapsed_time(e1) / reps
 
 
-def run(name, nel, K, radii, offsets, out):
-    x_a, z_a = rs.transducer(num_elements=nel)
+def run(name, nel, K, radii, offsets, out, pitch=None, fp32=True):
+    x_a, z_a = rs.transducer(num_elements=nel) if pitch is None else rs.transducer(num_elements=nel, pitch=np.float64(pitch))
     alpha, zf = rs.launch_angles(K), rs.focus_line(K)
     eng = TofEngine(0).setup(alpha, zf, x_a[nel // 2], z_a[nel // 2], x_a)
     r, o = torch.from_numpy(np.ascontiguousarray(radii)).cuda(), torch.from_numpy(np.ascontiguousarray(offsets)).cuda()
@@ -31,6 +31,10 @@ def run(name, nel, K, radii, offsets, out):
         res[mode + "_ray_solves_per_s"] = E * G / (ms * 1e-3)
     res["hits"] = int((kh >= 0).sum())
     eng.set_search("guided")
+    if not fp32:
+        out[name] = res
+        eng.close()
+        return
     tof32 = torch.empty((G, E), dtype=torch.float32, device="cuda"); kh32 = torch.empty_like(kh)
     t32, ms32 = timed(lambda: eng.tof_table_f32_cuda(r, o, out_tof=tof32, out_k_hit=kh32))
     same = (kh >= 0) & (kh == kh32)
@@ -50,6 +54,8 @@ run("config2_64el_512x512", 64, 905, *rs.synthetic_grid(512, 512), out)
 run("config3_128el_1024x1024", 128, 905, *rs.synthetic_grid(1024, 1024), out)
 run("sensitivity_K1810_128el_256x256", 128, 1810, *rs.synthetic_grid(256, 256), out)
 run("sensitivity_K4096_128el_128x128", 128, 4096, *rs.synthetic_grid(128, 128), out)
+# many receivers: the first-hit state no longer fits shared memory and lives in the output rows (HG instantiation)
+run("large_E_1025_receivers_128x128_HG", 1024, 905, *rs.synthetic_grid(128, 128), out, pitch=0.04 / 1024, fp32=False)
 if "--big" in sys.argv:
     run("config4_128el_4096x4096_one_gpu", 128, 905, *rs.synthetic_grid(4096, 4096), out)
 print(json.dumps(out, indent=1))

@@ -26,17 +26,18 @@ LIB = os.path.join(ROOT, "ray_tracing_ultrasound_b200", "libtofrt.so")
 MARKERS = {
     "tofrt_table_kernel": [
         ("tofrt_table_kernel(DevSetup S, TableArgs T)", "kernel prologue (staging, TMA)"),
-        ("__shared__ unsigned long long s_base;", "per-geometry setup (work fetch, state reset)"),
-        ("// ---- main_rt.py:351-364 pipe intersection", "stage 2a: pipe intersection (main_rt.py:351-364)"),
-        ("// ---- main_rt.py:367-376 reflection", "stage 2b: reflection, atan, tan (main_rt.py:367-376)"),
+        ("__shared__ unsigned long long s_base;", "per-geometry setup, chunk loop head, ray-table loads"),
+        ("// ---- main_rt.py:351-364 pipe intersection, upper root; :367-376 reflection", "stage 2: pipe intersection + reflection, vector form (main_rt.py:351-376)"),
+        ("// ---- main_rt.py:351-364 pipe intersection, upper root ----", "stage 2 in the reference's angle form (main_rt.py:351-376)"),
+        ("if (T.inject_m)", "test hook"),
         ("// ---- main_rt.py:78-99 first sign change", "return-path search (main_rt.py:78-99)"),
-        ("int flagged = -1;", "scan fallback / literal scan + on-sample rule"),
-        ("double ix = NAN, iz = NAN;", "chord intersection (main_rt.py:106-168)"),
+        ("int flagged = -1;", "exact scans / literal scan + on-sample rule"),
+        ("// chord intersection for every lane", "chord intersection (main_rt.py:106-168)"),
         ("// ---- main_rt.py:396-405 refraction back", "stage 4: second refraction, landing point (main_rt.py:396-405)"),
         ("// ---- optional per-ray records", "ray records"),
         ("// ---- main_rt.py:487-501 which receivers", "table assembly (main_rt.py:487-501)"),
-        ("// ---- one geometry done", "row store"),
-        ("if (T.stats) {", "epilogue"),
+        ("// ---- one geometry done", "row store / hit emission"),
+        ("if (STATS && T.stats) {", "epilogue"),
     ],
     "tofrt_fermat3d_kernel": [
         ("tofrt_fermat3d_kernel(tofrt_surf3d S, F3dArgs A)", "prologue / work fetch / staging"),
@@ -114,7 +115,7 @@ def main():
                 if line[1] >= ln:
                     name = nm
         if name is None and line and os.path.basename(line[0]).startswith("tofrt_"):
-            name = "out-of-line helpers (scan_exact_from)"
+            name = "out-of-line helpers, division / square-root slow paths"
             agg.setdefault(name, [0, 0, 0])
         if name is None:
             unknown[0] += ns; unknown[1] += ni

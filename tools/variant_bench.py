@@ -5,7 +5,9 @@
 import os, subprocess, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = {"c16": ("TOFRT_SCAN_CHUNK=16",), "c32": ("TOFRT_SCAN_CHUNK=32",), "c8": ("TOFRT_SCAN_CHUNK=8",)}
+VARIANTS = {"base": (), "t896": ("TOFRT_THREADS_GUIDED=896",), "t768": ("TOFRT_THREADS_GUIDED=768",),
+            "t512x2": ("TOFRT_THREADS_GUIDED=512", "TOFRT_MIN_BLOCKS=2"), "w8": ("TOFRT_PRED_W=8", "TOFRT_PRED_STEPS=4"),
+            "w2": ("TOFRT_PRED_W=2", "TOFRT_PRED_STEPS=2")}
 VDIR = os.path.join(ROOT, "tools", "_variants")
 
 if sys.argv[1] == "build":
@@ -28,7 +30,7 @@ else:
     radii, offsets = rs.synthetic_grid(256, 1024)
     r = torch.from_numpy(radii).cuda(); o = torch.from_numpy(offsets).cuda()
     out = {"variant": sys.argv[2], "info": eng.kernel_info()}
-    for mode in ("guided", "scan", "guided+vector", "scan+vector"):
+    for mode in ("guided+vector",):
         eng.set_search(mode.split("+")[0])
         eng.set_math("vector" if "+vector" in mode else "angle")
         for _ in range(4): eng.tof_table_cuda(r, o)
