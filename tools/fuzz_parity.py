@@ -111,4 +111,35 @@ out["fermat3d_vs_twin"] = {"pairs": int(tg.size), "same_start_sample_frac": floa
                            "max_abs_dt_other_start_s": float(np.abs(tg - tt)[~same].max(initial=0.0)),
                            "max_grid_gap_other_start_s": float(gap[~same].max(initial=0.0)),
                            "max_newton_evaluations": int(ev.max()), "seconds": round(time.time() - t0, 1)}
+# (5) the fused hit emission (tofrt_hits_host, pipelined chunks) against the dense table on random geometries
+eng.setup(alpha, zf, x_a[64], z_a[64], x_a); eng.set_search("guided"); eng.set_math("vector")
+n7 = int(os.environ.get("FUZZ_HITS_GEOMS", "1000000"))
+r7, o7 = rng.uniform(0.002, 0.15, n7), rng.uniform(-0.04, 0.04, n7)
+t0 = time.time()
+dense = eng.tof_table_cuda(torch.from_numpy(r7).cuda(), torch.from_numpy(o7).cuda())
+hg, he, hk, ht = eng.tof_hits(r7, o7)
+gg, ee = torch.nonzero(dense.k_hit >= 0, as_tuple=True)
+out["hit_list_vs_dense"] = {"geometries": n7, "hits": int(len(hg)),
+                            "identical": bool(len(hg) == len(gg) and np.array_equal(hg, gg.cpu().numpy()) and
+                                              np.array_equal(he, ee.cpu().numpy()) and
+                                              np.array_equal(hk, dense.k_hit[gg, ee].cpu().numpy()) and
+                                              np.array_equal(ht, dense.tof[gg, ee].cpu().numpy())),
+                            "seconds": round(time.time() - t0, 1)}
+del dense, gg, ee
+# (6) small-G latency mode (CTA per geometry) against the regular kernel on many small random batches
+n8 = int(os.environ.get("FUZZ_SMALLG_BATCHES", "400"))
+bad = 0; tot = 0; t0 = time.time()
+for i in range(n8):
+    n = int(rng.integers(1, 400))
+    r8 = torch.from_numpy(rng.uniform(0.002, 0.15, n)).cuda(); o8 = torch.from_numpy(rng.uniform(-0.04, 0.04, n)).cuda()
+    eng.set_small_g(True); a = eng.tof_table_cuda(r8, o8, records=("idx", "target_x"))
+    eng.set_small_g(False); b = eng.tof_table_cuda(r8, o8, records=("idx", "target_x"))
+    torch.cuda.synchronize()
+    ta, tb = a.records["target_x"], b.records["target_x"]
+    bad += int((a.tof != b.tof).sum()) + int((a.k_hit != b.k_hit).sum()) + int((a.records["idx"] != b.records["idx"]).sum())
+    bad += int(((ta != tb) & ~(ta.isnan() & tb.isnan())).sum())
+    tot += n
+eng.set_small_g(True)
+out["small_g_vs_regular_kernel"] = {"batches": n8, "geometries": tot, "rays": tot * len(alpha), "mismatches": bad,
+                                    "seconds": round(time.time() - t0, 1)}
 print(json.dumps(out, indent=1))
