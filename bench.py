@@ -611,7 +611,23 @@ def main():
             out["all_gather"] = gather_info
         if not args.no_cpu:
             v, threads, n, dt = cpu_port_rate(x_a, z_a, alpha, zf, radii, offsets)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            numpy_leg = None
+            try:   # the reference's NumPy CPU path (N = 1 runs only)
+                if world > 1:
+                    raise RuntimeError("measured on single-GPU runs only"): its expressions vectorised over the rays of a shot (oracle/oracle_numpy.py)
+                from oracle import oracle_numpy
+                procs = max(1, min(threads, os.cpu_count() or 1))
+                ngeo = 48 * procs
+                sel = np.linspace(0, G - 1, ngeo).astype(np.int64)
+                nv, ndt = oracle_numpy.timed_rate(x_a, z_a, zf, alpha, N_ELEM // 2, radii[sel], offsets[sel], procs)
+                numpy_leg = {"value": nv, "unit": UNIT, "cores": procs, "kind": "port",
+                             "sample": f"{ngeo} of {G} geometries, evenly strided, {ndt:.1f} s, {procs} processes",
+                             "note": "main_rt.py's own NumPy expressions in its operation order, vectorised over the K rays "
+                                     "of a shot (K x N diffs matrix, K x E np.isclose) instead of Python loops; the verbatim "
+                                     "script does 35.6 ray-solves/s per core (BASELINE.md) and cannot travel to the GPU box"}
+            except Exception as exc:   # the baseline must never take the bench line down
+                numpy_leg = {"unavailable": repr(exc)}
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "numpy": numpy_leg,
                                    "note": "C restatement of main_rt.py (oracle/), pthreads over geometries; the reference's "
                                            "own NumPy path measured 35.6 ray-solves/s on one core of the build container "
                                            "(BASELINE.md section 2) and cannot travel to the GPU box",
