@@ -441,34 +441,39 @@ int tofrt_setup_shooters(tofrt_ctx *c, const tofrt_params *p, const double *alph
     // ---- FP32 mode: the same tables rounded to float ----
     {
         const int Es = std::max(1, S.E_sorted);
-        const size_t nf = (size_t)4 * K + (size_t)6 * K * NS + K + E + Es;  // lens(2K) seg(2K) [a,b,phi,cos,sin,leg1](S*K) zf x_rx xs
+        const size_t n_ray_t = (size_t)kRayPlanes * S.C * 32 * NS;
+        const size_t nf = (size_t)4 * K + n_ray_t + (size_t)K * NS + E + Es;  // lens(2K) seg(2K) ray_t leg1(S*K) x_rx xs
         CUDA_TRY(cudaMalloc(&c->d_f32, sizeof(float) * nf));
         float *f = c->d_f32;
-        auto conv = [&](const double *src, int n) {
+        auto conv = [&](const double *src, size_t n) {
             float *dst = f;
-            if (n > 0) tofrt_to_float_kernel<<<(n + 255) / 256, 256>>>(n, src, dst);
+            if (n > 0) tofrt_to_float_kernel<<<(unsigned)((n + 255) / 256), 256>>>((int)n, src, dst);
             f += n;
             return dst;
         };
         DevSetupF F{};
-        F.lens = (const float2 *)conv((const double *)c->d_lens, 2 * K);
-        F.seg = (const float2 *)conv((const double *)c->d_seg, 2 * K - 2); f += 2;
-        F.a_pq = conv(c->d_a, K * NS); F.b_pq = conv(c->d_b, K * NS); F.phi_pq = conv(c->d_phi, K * NS);
-        F.cpq = conv(c->d_cs, K * NS); F.spq = conv(c->d_cs + (size_t)K * NS, K * NS);
-        F.z_f = conv(c->d_zf, K); F.leg1 = conv(c->d_leg1, K * NS);
+        F.lens = (const float2 *)conv((const double *)c->d_lens, 2 * (size_t)K);
+        F.seg = (const float2 *)conv((const double *)c->d_seg, 2 * (size_t)K - 2); f += 2;
+        F.ray_t = conv(c->d_ray_t, n_ray_t);
+        F.leg1 = conv(c->d_leg1, (size_t)K * NS);
         F.x_rx = conv(c->d_xrx, E); F.xs = conv(c->d_xs, S.E_sorted);
         CUDA_TRY(cudaGetLastError());
         F.perm = c->d_perm;
-        F.c1 = (float)S.c1; F.c2 = (float)S.c2; F.fourAC = (float)S.fourAC; F.twoA = (float)S.twoA;
-        F.twod = (float)S.twod; F.K2 = (float)S.K2; F.phi1 = (float)S.phi1; F.c1_over_c2 = (float)S.c1_over_c2;
+        F.bucket = c->d_bucket; F.nb = S.nb; F.bx0 = (float)S.bx0; F.binv = (float)S.binv;
+        F.c1 = (float)S.c1; F.c2 = (float)S.c2; F.fourAC = (float)S.fourAC; F.inv_twoA = (float)S.VL.inv_twoA;
+        F.twod = (float)S.twod; F.K2 = (float)S.K2; F.pt = (float)S.VL.pt; F.c1_over_c2 = (float)S.c1_over_c2;
         F.rtol = (float)S.rtol; F.atol = (float)S.atol;
         F.tol_max = (float)(S.tol_max * 1.001) + 1e-30f;
         F.rx_min = (float)S.rx_min; F.rx_max = (float)S.rx_max; F.X = (float)S.X * 1.0001f; F.Z = (float)S.Z * 1.0001f;
-        F.K = K; F.E = E; F.E_sorted = S.E_sorted; F.has_nonfinite_rx = S.has_nonfinite_rx;
+        F.K = K; F.C = S.C; F.E = E; F.E_sorted = S.E_sorted; F.has_nonfinite_rx = S.has_nonfinite_rx;
         F.shape = S.shape; F.log2n = S.log2n; F.n_shooters = NS; F.surface = S.surface; F.h0 = (float)S.h0;
+        F.P0 = make_float2((float)S.P0.x, (float)S.P0.y); F.PN = make_float2((float)S.PN.x, (float)S.PN.y);
+        // the cell table is only safe in float while a cell is wide against the rounding of a landing point
+        if (!(std::fabs(S.bx0) < 1e30 && S.binv < 1e30 && 1.0 / std::max(S.binv, 1e-300) > 64 * 1.2e-7 * std::max(std::fabs(S.rx_min), std::fabs(S.rx_max))))
+            F.nb = 0;
         c->SF = F;
         c->smem_f32 = (size_t)2 * K * sizeof(float2) + (size_t)S.E_sorted * (sizeof(float) + sizeof(int)) +
-                      (size_t)kWarps * E * (sizeof(float) + sizeof(int)) + 16;
+                      (size_t)kWarpsF32 * E * (sizeof(float) + sizeof(int)) + (size_t)F.nb * sizeof(int) + 16;
         if (c->smem_f32 > kMaxDynSmem) c->smem_f32 = 0;  // FP32 mode keeps its first-hit state in shared memory only
         else
             CUDA_TRY(cudaFuncSetAttribute(tofrt_table_kernel_f32, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -644,8 +649,8 @@ int tofrt_table_f32_dev(tofrt_ctx *c, const double *d_radius, const double *d_of
     cudaError_t ce;
     T.counter = c->take_counter(st, &ce);
     CUDA_TRY(ce);
-    int grid = (int)std::min<long long>((long long)c->sm_count, (G * c->n_shooters + kWarps - 1) / kWarps);
-    tofrt_table_kernel_f32<<<grid, kThreads, c->smem_f32, st>>>(c->SF, T);
+    int grid = (int)std::min<long long>((long long)c->sm_count, (G * c->n_shooters + kWarpsF32 - 1) / kWarpsF32);
+    tofrt_table_kernel_f32<<<grid, kThreadsF32, c->smem_f32, st>>>(c->SF, T);
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
 }
