@@ -612,9 +612,9 @@ def main():
         if not args.no_cpu:
             v, threads, n, dt = cpu_port_rate(x_a, z_a, alpha, zf, radii, offsets)
             numpy_leg = None
-            try:   # the reference's NumPy CPU path (N = 1 runs only)
+            try:   # the reference's NumPy CPU path: its expressions vectorised over the rays of a shot (oracle/oracle_numpy.py)
                 if world > 1:
-                    raise RuntimeError("measured on single-GPU runs only"): its expressions vectorised over the rays of a shot (oracle/oracle_numpy.py)
+                    raise RuntimeError("measured on single-GPU runs only")
                 from oracle import oracle_numpy
                 procs = max(1, min(threads, os.cpu_count() or 1))
                 ngeo = 48 * procs
