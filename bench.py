@@ -20,10 +20,10 @@ K = N = 905 launch rays / lens samples:
             inside the timed region.  --e2e-form sparse (default): tofrt_hits_host, the list of the table's hits
             (every other entry is `False, 0`: the complete result); dense: tofrt_table_host, the full table.  The
             other form is reported beside it.
-`roofline`: FP64 instruction issue.  `frac_vs_reference_algorithm` = algorithmic FP64 ops of SURVEY section 8(d) (the
-            reference's full N-sample scan per ray) per launch / launch time / peak; `frac_executed` = FP64 operations
-            the kernel actually executed (counted by the instrumented instantiation of the same kernel, outside the
-            timed region) / launch time / peak.  peak = FP64 instruction rate measured on this GPU by
+`roofline`: FP64 instruction issue.  `frac` = FP64-pipe instructions the kernel executed (counted by the instrumented
+            instantiation of the same kernel, outside the timed region) / launch time / peak; `frac_executed` = the same
+            with useful operations (division, square root = 1) instead of instructions; `frac_vs_reference_algorithm` =
+            algorithmic FP64 ops of SURVEY section 8(d) (the reference's full N-sample scan per ray) / launch time / peak.  peak = FP64 instruction rate measured on this GPU by
             tofrt_measure_fp64_peak (MEASURED_PEAKS.json has no FP64 entry).  The hardware-side figure (FP64-pipe
             utilisation from ncu) is quoted from profiles/ only when the capture belongs to this very source.
 `cpu_baseline`: the oracle port (C, all host threads) on a bounded sample.
@@ -62,6 +62,21 @@ OPS = {
 }
 
 
+# FP64-pipe INSTRUCTIONS per item of the same kernel (a division is 9 of them, a square root 8, a comparison 1), read
+# off the per-line SASS table of the profiled build (tools/line_breakdown.py on profiles' guided capture).  With the
+# counters of the instrumented launch they reproduce ncu's sm__inst_executed_pipe_fp64 of that build to within 4 %.
+FP64_INST = {
+    "ray": 51,                 # pipe 19, reflect 18, m 9, b 1, cell index 4
+    "fast_ray": 31,            # tol, end diffs, certainty tests, probe constants
+    "probe": 3,                # DFMA + 2 DSETP
+    "exact_diff": 6,           # DMUL, DADD, DADD + sign tests
+    "lens2_ray": 69,           # chord intersection 28, tofrt_vec_return_head 41
+    "landing_ray": 26,         # tofrt_vec_return_tail
+    "receiver_test": 5,
+    "winner_ray": 54,
+}
+
+
 def source_hash():
     """sha256 over the CUDA sources + the C header: stamps ncu captures (tools/ncu_summary.py) to the build they profile."""
     h = hashlib.sha256()
@@ -95,12 +110,14 @@ def algorithmic_ops(G, K, N, E):
     return float(G) * (K * (155.0 + 3.0 * N) + 2.0 * E * K)
 
 
-def executed_ops(st):
-    """FP64 operations the table kernel executed, from the instrumented launch's counters (TofEngine.last_stats)."""
-    return float(OPS["ray"] * st["rays"] + OPS["fast_ray"] * (st["bracket_rays"] + st["scan_rays"]) +
-                 OPS["probe"] * st["probes"] + OPS["exact_diff"] * st["exact_diffs"] + OPS["lens2_ray"] * st["lens2_rays"] +
-                 OPS["landing_ray"] * st["landing_rays"] + OPS["receiver_test"] * st["receiver_tests"] +
-                 OPS["winner_ray"] * st["winner_rays"])
+def executed_ops(st, per_item=None):
+    """FP64 operations (per_item = OPS) or FP64-pipe instructions (per_item = FP64_INST) the table kernel executed,
+    from the instrumented launch's counters (TofEngine.last_stats)."""
+    w = per_item or OPS
+    return float(w["ray"] * st["rays"] + w["fast_ray"] * (st["bracket_rays"] + st["scan_rays"]) +
+                 w["probe"] * st["probes"] + w["exact_diff"] * st["exact_diffs"] + w["lens2_ray"] * st["lens2_rays"] +
+                 w["landing_ray"] * st["landing_rays"] + w["receiver_test"] * st["receiver_tests"] +
+                 w["winner_ray"] * st["winner_rays"])
 
 
 class ClockSampler(threading.Thread):
@@ -538,22 +555,29 @@ def main():
         kern_s = float(np.mean(launch_ms)) * 1e-3
         ops_ref = algorithmic_ops(G, K, K, E)
         ops_exec = executed_ops(stats)
+        inst_exec = executed_ops(stats, FP64_INST)
         roofline = {
             "bound": "fp64-issue", "kernel": "tofrt_table_kernel", "kernel_ms": kern_s * 1e3, "search": args.search,
             "peak": peak_issue / 1e12, "unit": "TFLOP/s",
             "peak_source": "tofrt_measure_fp64_peak on this GPU (un-fused DMUL+DADD thread-instructions/s); "
                            "MEASURED_PEAKS.json holds no FP64 figure",
             "peak_dfma_tflops": 2 * peak_fma / 1e12,
-            # executed: what this kernel really computes
-            "achieved": ops_exec / kern_s / 1e12, "frac": ops_exec / kern_s / peak_issue,
+            # executed FP64-pipe instructions / time / measured FP64 instruction peak: the pipe's utilisation (guided mode)
+            "achieved": inst_exec / kern_s / 1e12, "frac": inst_exec / kern_s / peak_issue,
+            "frac_fp64_instructions": inst_exec / kern_s / peak_issue, "executed_fp64_instructions_per_launch": inst_exec,
+            "fp64_instructions_per_item": FP64_INST,
+            # executed useful operations (a division or square root = 1): lower bound of the above
             "frac_executed": ops_exec / kern_s / peak_issue, "executed_fp64_ops_per_launch": ops_exec,
             "executed_counters": stats, "ops_per_item": OPS,
             # the reference's algorithm (full N-sample scan per ray) done in this time
             "frac_vs_reference_algorithm": ops_ref / kern_s / peak_issue, "algorithmic_ops_per_launch": ops_ref,
             "traffic": None, "table_write_gbs": G * E * 12 / kern_s / 1e9,
-            "note": "frac = frac_executed: FP64 operations the kernel executed (counters of the instrumented instantiation x "
-                    "the per-item operation counts in ops_per_item; a division or square root counts as ONE operation although "
-                    "it issues ~9 FP64 instructions, so this is a lower bound of the pipe's utilisation) / launch time / peak.  "
+            "note": "frac = frac_fp64_instructions: FP64-pipe instructions the timed kernel executed (counters of the instrumented "
+                    "instantiation of the same kernel, run outside the timed region, x the per-item instruction counts read off "
+                    "the SASS: fp64_instructions_per_item) / launch time / measured FP64 instruction peak -- the in-run twin of "
+                    "ncu's sm__inst_executed_pipe_fp64 (roofline.ncu, quoted when the capture belongs to this source).  "
+                    "frac_executed counts useful operations instead (ops_per_item; a division or square root = ONE operation "
+                    "although it issues ~9 FP64 instructions): a lower bound.  "
                     "frac_vs_reference_algorithm uses SURVEY 8(d)'s count G*(K*(155+3N)+2EK), i.e. the reference's full "
                     "N-sample scan per ray, which the guided search provably skips: it exceeds 1 and is a speed-up over "
                     "the reference algorithm at the roofline, not a utilisation.",
@@ -579,7 +603,9 @@ def main():
             o_s = extras["other_ms"] * 1e-3
             roofline["roofline_" + extras["other"]] = {
                 "kernel_ms": extras["other_ms"], "frac_vs_reference_algorithm": ops_ref / o_s / peak_issue,
-                "frac_executed": executed_ops(extras["other_stats"]) / o_s / peak_issue, "modes_identical": extras["other_same"]}
+                "frac_executed": executed_ops(extras["other_stats"]) / o_s / peak_issue, "modes_identical": extras["other_same"],
+                "note": "the other search mode, same outputs bit for bit; for the literal scan every exact diff is 3 FP64 "
+                        "operations and the SURVEY 8(d) count is the like-for-like one"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
