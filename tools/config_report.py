@@ -56,6 +56,24 @@ run("sensitivity_K1810_128el_256x256", 128, 1810, *rs.synthetic_grid(256, 256), 
 run("sensitivity_K4096_128el_128x128", 128, 4096, *rs.synthetic_grid(128, 128), out)
 # many receivers: the first-hit state no longer fits shared memory and lives in the output rows (HG instantiation)
 run("large_E_1025_receivers_128x128_HG", 1024, 905, *rs.synthetic_grid(128, 128), out, pitch=0.04 / 1024, fp32=False)
+# SURVEY row f2, full-matrix capture: every element shoots (S = E); stage-1 quantities per (shooter, ray), table [S][G][E]
+def run_full_matrix(name, nel, K, radii, offsets, out):
+    x_a, z_a = rs.transducer(num_elements=nel)
+    alpha, zf = rs.launch_angles(K), rs.focus_line(K)
+    eng = TofEngine(0).setup(alpha, zf, x_a, z_a, x_a)
+    r, o = torch.from_numpy(np.ascontiguousarray(radii)).cuda(), torch.from_numpy(np.ascontiguousarray(offsets)).cuda()
+    G, E = len(radii), len(x_a)
+    tof = torch.empty((E, G, E), dtype=torch.float64, device="cuda"); kh = torch.empty((E, G, E), dtype=torch.int32, device="cuda")
+    t, ms = timed(lambda: eng.tof_table_cuda(r, o, out_tof=tof, out_k_hit=kh))
+    # the centre shooter's block against the single-shooter setup
+    one = TofEngine(0).setup(alpha, zf, x_a[nel // 2], z_a[nel // 2], x_a).tof_table_cuda(r, o)
+    out[name] = {"S": E, "E": E, "K": K, "G": G, "ray_solves": E * E * G, "guided_ms": ms,
+                 "guided_ray_solves_per_s": E * E * G / (ms * 1e-3), "hits": int((kh >= 0).sum()),
+                 "centre_shooter_block_equals_single_shooter_call": bool((tof[nel // 2] == one.tof).all() and (kh[nel // 2] == one.k_hit).all())}
+    eng.close()
+
+
+run_full_matrix("full_matrix_capture_129_shooters_64x64", 128, 905, *rs.synthetic_grid(64, 64), out)
 if "--big" in sys.argv:
     run("config4_128el_4096x4096_one_gpu", 128, 905, *rs.synthetic_grid(4096, 4096), out)
 print(json.dumps(out, indent=1))
