@@ -517,6 +517,33 @@ def test_sparse_hit_list_equals_dense_table(engine):
     assert all(len(a) == 0 for a in engine.tof_hits([], []))
 
 
+def test_sparse_hit_list_pipeline_many_chunks_and_slot_overflow(engine, monkeypatch):
+    """tofrt_hits_host's chunked pipeline: 11 chunks through the ring of three buffers with a ragged last chunk,
+    several shooters across chunk boundaries, a capacity smaller than the result -- and the fallback to the dense route
+    when a row holds more hits than its 16-entry slot (a tolerance wide enough that a ray lands on many receivers)."""
+    monkeypatch.setenv("TOFRT_HIT_CHUNK_ROWS", "1024")
+    x_a, z_a, alpha, zf = _std(engine)
+    radii, offsets = rs.synthetic_grid(131, 83)          # 10 873 rows = 10 chunks of 1 024 + 633
+
+    def check(t, hits, n_geoms):
+        g, e, k, tof = hits
+        nz = np.nonzero(t.hit)
+        rows = nz[0] if t.hit.ndim == 2 else nz[0] * n_geoms + nz[1]
+        assert len(g) == len(rows) > 1000
+        assert np.array_equal(g, rows) and np.array_equal(e, nz[-1])
+        assert np.array_equal(k, t.k_hit[nz]) and np.array_equal(tof, t.tof[nz])
+
+    t = engine.tof_table(radii, offsets)
+    check(t, engine.tof_hits(radii, offsets), len(radii))
+    check(t, engine.tof_hits(radii, offsets, capacity=777), len(radii))
+    engine.setup(alpha, zf, x_a[31:34], z_a[31:34], x_a)  # rows = 3 x 4 000: shooters change inside a chunk
+    check(engine.tof_table(radii[:4000], offsets[:4000]), engine.tof_hits(radii[:4000], offsets[:4000]), 4000)
+    _std(engine, atol=3e-3)                               # +-3 mm: ~20 of the 65 receivers match one landing point
+    t = engine.tof_table(radii[:3000], offsets[:3000])
+    assert int(t.hit.sum(axis=1).max()) > 16
+    check(t, engine.tof_hits(radii[:3000], offsets[:3000]), 3000)
+
+
 def test_host_pipeline_many_chunks_with_records(engine):
     """The host path cuts the geometries into ~64 MB chunks (double-buffered); with per-ray records a
     chunk is only ~1 600 geometries, so 5 000 geometries exercise several chunks, the slot reuse and
