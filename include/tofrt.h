@@ -193,7 +193,8 @@ int tofrt_table_f32_dev(tofrt_ctx *ctx, const double *d_radius, const double *d_
  * point minimising |A_e - P(alpha)|/c1 + |P(alpha) - F|/c2 over the lens of the current setup
  * (h_from_alpha / dh_from_alpha, main_rt.py:180-214): kmin = discrete argmin over the lens
  * samples, tof = travel time at the refined stationary point, alpha = refined entry angle
- * (may be NULL).  Element-major outputs: tof[e*F + f]. */
+ * (may be NULL).  Element-major outputs: tof[e*F + f].  Bit-identical to the oracle's CPU twin of the same
+ * operations (oracle/tofrt_oracle.c: tofo_fermat2d). */
 int tofrt_fermat_dev(tofrt_ctx *ctx, const double *d_fx, const double *d_fz, long long F, double *d_tof,
                      int *d_kmin, double *d_alpha, void *stream);
 int tofrt_fermat_host(tofrt_ctx *ctx, const double *fx, const double *fz, long long F, double *tof,
@@ -216,6 +217,12 @@ int tofrt_fermat_host(tofrt_ctx *ctx, const double *fx, const double *fz, long l
  *                          the refined result is the same); ab[2*(e*F + f) + {0,1}] = refined
  *                          entry angles.  kmin and ab may be NULL.
  *   tofrt_fermat3d_host    host pointers, chunked and pipelined like tofrt_table_host.
+ * In-plane rule: a pair whose element and voxel both have y == 0 IS the 2-D problem of the current setup and is
+ * solved by tofrt_fermat_dev's arithmetic (its K lens samples, its refinement), so the plane y = 0 of a
+ * matrix-array table equals the linear-array table bit for bit (SURVEY.md 8(d), config 5's consistency pin); such
+ * a pair reports kmin = -1 - j (j = its 2-D lens sample) and ab = (alpha, 0).  The rule applies when the 3-D
+ * aperture equals the 2-D one (ang[0] == alpha[0], ang[n_side-1] == alpha[K-1]); otherwise every pair takes the
+ * 3-D search.
  * Checked against tests/fermat3d_oracle.py (NumPy/SciPy), the oracle's bit-exact twin, the 2-D
  * solver in the plane y = 0 and analytic known answers (tests/test_gpu_fermat3d.py). */
 int tofrt_fermat3d_setup(tofrt_ctx *ctx, const double *ang, int n_side, const double *ex, const double *ey,

@@ -128,8 +128,20 @@ class Oracle:
         return (tof, k_hit, idx, margin) if want_margin else (tof, k_hit, idx)
 
     # ---- 3-D two-point Fermat solve: CPU twin of the CUDA kernel (device-math build only) ----
-    def fermat3d(self, p, ang, ex, ey, z_el, fx, fy, fz):
-        """-> tof[E][F], kmin[E][F], ab[E][F][2], evals[E][F], gap[E][F]."""
+    def fermat2d(self, p, alpha, x_el, z_el, fx, fz):
+        """2-D two-point solve, CPU twin of the CUDA kernel -> tof[E][F], kmin[E][F], alpha[E][F]."""
+        assert self.device_math, "the 2-D two-point twin exists in the device-math build only"
+        alpha, x_el, fx, fz = map(_f64, (alpha, x_el, fx, fz))
+        E, F = len(x_el), len(fx)
+        tof, kmin, al = np.empty((E, F)), np.empty((E, F), dtype=np.int32), np.empty((E, F))
+        rc = self.lib.tofo_fermat2d(ctypes.byref(p), _dp(alpha), ctypes.c_int(len(alpha)), _dp(x_el), ctypes.c_int(E),
+                                    ctypes.c_double(z_el), _dp(fx), _dp(fz), ctypes.c_int(F), _dp(tof), _ip(kmin), _dp(al))
+        assert rc == 0, rc
+        return tof, kmin, al
+
+    def fermat3d(self, p, ang, ex, ey, z_el, fx, fy, fz, alpha2d=None):
+        """-> tof[E][F], kmin[E][F], ab[E][F][2], evals[E][F], gap[E][F].  alpha2d: the 2-D setup's lens angles --
+        pairs in the plane y = 0 are then solved by the 2-D solver, as the product does (kmin = -1 - j)."""
         assert self.device_math, "the 3-D twin exists in the device-math build only"
         ang, ex, ey, fx, fy, fz = map(_f64, (ang, ex, ey, fx, fy, fz))
         E, F = len(ex), len(fx)
@@ -137,7 +149,9 @@ class Oracle:
         ab, evals, gap = np.empty((E, F, 2)), np.empty((E, F), dtype=np.int32), np.empty((E, F))
         rc = self.lib.tofo_fermat3d(ctypes.byref(p), _dp(ang), ctypes.c_int(len(ang)), _dp(ex), _dp(ey),
                                     ctypes.c_int(E), ctypes.c_double(z_el), _dp(fx), _dp(fy), _dp(fz),
-                                    ctypes.c_int(F), _dp(tof), _ip(kmin), _dp(ab), _ip(evals), _dp(gap))
+                                    ctypes.c_int(F), _dp(tof), _ip(kmin), _dp(ab), _ip(evals), _dp(gap),
+                                    _dp(_f64(alpha2d)) if alpha2d is not None else None,
+                                    ctypes.c_int(0 if alpha2d is None else len(alpha2d)))
         assert rc == 0, rc
         return tof, kmin, ab, evals, gap
 

@@ -51,6 +51,56 @@ __device__ __forceinline__ void fermat_eval(const DevSetup &S, double al, double
     *dt = (u1x * dx + u1z * dz) / (S.c1 * r1) + (u2x * dx + u2z * dz) / (S.c2 * r2);
 }
 
+// Continuous refinement of one pair from its discrete minimiser: safeguarded secant (Illinois) on dt/dalpha inside
+// the two sample intervals around lens sample jbest.  Shared by the 2-D kernel and the in-plane pairs of the 3-D one.
+__device__ __forceinline__ void fermat2d_refine(const DevSetup &S, const double *alpha, int N, int jbest, double ax,
+                                                double az, double fx, double fz, double *tof_out, double *al_out)
+{
+    double a = alpha[max(jbest - 1, 0)], b = alpha[min(jbest + 1, N - 1)];
+    double ta, ga, tb, gb, tc, gc;
+    fermat_eval(S, a, ax, az, fx, fz, &ta, &ga);
+    fermat_eval(S, b, ax, az, fx, fz, &tb, &gb);
+    double al = alpha[jbest], tof;
+    fermat_eval(S, al, ax, az, fx, fz, &tof, &gc);
+    if (ga < 0.0 && gb > 0.0) {  // a bracketed stationary point: Illinois false position on dt/dalpha
+        int side = 0;
+        for (int it = 0; it < 8; ++it) {
+            double c = (a * gb - b * ga) / (gb - ga);
+            if (!(c > a && c < b)) c = 0.5 * (a + b);
+            fermat_eval(S, c, ax, az, fx, fz, &tc, &gc);
+            al = c; tof = tc;
+            if (gc == 0.0) break;
+            if (gc > 0.0) { b = c; gb = gc; if (side == 1) ga *= 0.5; side = 1; }
+            else { a = c; ga = gc; if (side == -1) gb *= 0.5; side = -1; }
+        }
+    }
+    *tof_out = tof; *al_out = al;
+}
+
+// One whole pair of the 2-D solve without the kernel's staging: exact FP64 argmin over the lens samples in global
+// memory (|A - P_j| / c1 evaluated on the fly with the expression of tofrt_fermat_d1_kernel), then the refinement.
+// Same operations, hence the same bits, as tofrt_fermat_kernel computes for this pair.  Used by the 3-D kernel for
+// pairs that lie in the plane y = 0 (out of line: its registers are not the 3-D kernel's).
+__device__ __noinline__ double2 fermat2d_pair(const DevSetup &S, const double *alpha, double ax, double az, double fx,
+                                              double fz, int *jbest_out)
+{
+    const int N = S.K;
+    const double inv_c2 = 1.0 / S.c2;
+    double best = INFINITY;
+    int jbest = 0;
+    for (int j = 0; j < N; ++j) {
+        const double2 q = S.lens[j];
+        const double d1 = dist2d(ax, az, q.x, q.y) / S.c1;
+        const double ux = q.x - fx, uz = q.y - fz;
+        const double t = fma(sqrt(fma(ux, ux, uz * uz)), inv_c2, d1);
+        if (t < best) { best = t; jbest = j; }
+    }
+    double tof, al;
+    fermat2d_refine(S, alpha, N, jbest, ax, az, fx, fz, &tof, &al);
+    *jbest_out = jbest;
+    return make_double2(tof, al);
+}
+
 __global__ void __launch_bounds__(kFermatThreads) tofrt_fermat_kernel(DevSetup S, FermatArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,24 +179,8 @@ __global__ void __launch_bounds__(kFermatThreads) tofrt_fermat_kernel(DevSetup S
             }
         }
         // ---- continuous refinement between the neighbouring samples ----
-        double a = A.alpha[max(jbest - 1, 0)], b = A.alpha[min(jbest + 1, N - 1)];
-        double ta, ga, tb, gb, tc, gc;
-        fermat_eval(S, a, ax, az, fx, fz, &ta, &ga);
-        fermat_eval(S, b, ax, az, fx, fz, &tb, &gb);
-        double al = A.alpha[jbest], tof;
-        fermat_eval(S, al, ax, az, fx, fz, &tof, &gc);
-        if (ga < 0.0 && gb > 0.0) {  // a bracketed stationary point: Illinois false position on dt/dalpha
-            int side = 0;
-            for (int it = 0; it < 8; ++it) {
-                double c = (a * gb - b * ga) / (gb - ga);
-                if (!(c > a && c < b)) c = 0.5 * (a + b);
-                fermat_eval(S, c, ax, az, fx, fz, &tc, &gc);
-                al = c; tof = tc;
-                if (gc == 0.0) break;
-                if (gc > 0.0) { b = c; gb = gc; if (side == 1) ga *= 0.5; side = 1; }
-                else { a = c; ga = gc; if (side == -1) gb *= 0.5; side = -1; }
-            }
-        }
+        double al, tof;
+        fermat2d_refine(S, A.alpha, N, jbest, ax, az, fx, fz, &tof, &al);
         const size_t o = (size_t)e * A.F + f;
         A.tof[o] = tof;
         A.kmin[o] = jbest;
@@ -182,6 +216,11 @@ struct F3dArgs {
     double *tof;                 // [E][F]
     int *kmin;                   // [E][F] or null
     double *ab;                  // [E][F][2] or null
+    // In-plane pairs (element and voxel both at y = 0) are the 2-D problem of the current 2-D setup and are solved by
+    // its arithmetic, so that the plane y = 0 of a matrix-array table IS the linear-array table, bit for bit (SURVEY
+    // 8(d) config 5's consistency pin): alpha2d = the 2-D setup's lens angles (null: the apertures differ, no dispatch).
+    // Such a pair reports kmin = -1 - j (j = its 2-D lens sample) and ab = (alpha, 0).
+    const double *alpha2d;
     unsigned long long *counter;
 };
 
@@ -197,7 +236,8 @@ __global__ void tofrt_f3d_prepare_kernel(tofrt_surf3d S, F3dArgs A, float4 *smp)
     smp[(size_t)e * ns + s] = make_float4((float)P[0], (float)P[1], (float)P[2], (float)d1);
 }
 
-__global__ void __launch_bounds__(kF3dThreads, TOFRT_F3D_MIN_BLOCKS) tofrt_fermat3d_kernel(tofrt_surf3d S, F3dArgs A)
+__global__ void __launch_bounds__(kF3dThreads, TOFRT_F3D_MIN_BLOCKS)
+    tofrt_fermat3d_kernel(tofrt_surf3d S, F3dArgs A, const __grid_constant__ DevSetup S2)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *s_smp = reinterpret_cast<float4 *>(smem_raw);
@@ -225,6 +265,15 @@ __global__ void __launch_bounds__(kF3dThreads, TOFRT_F3D_MIN_BLOCKS) tofrt_ferma
         if (f >= A.F) continue;
         const double Fp[3] = {A.fx[f], A.fy[f], A.fz[f]};
         const double Ap[3] = {A.ex[e], A.ey[e], A.z_el};
+        if (A.alpha2d && Ap[1] == 0.0 && Fp[1] == 0.0) {  // in-plane pair: the 2-D solve (see F3dArgs)
+            int j2;
+            const double2 r = fermat2d_pair(S2, A.alpha2d, Ap[0], Ap[2], Fp[0], Fp[2], &j2);
+            const size_t o2 = (size_t)e * A.F + f;
+            A.tof[o2] = r.x;
+            if (A.kmin) A.kmin[o2] = -1 - j2;
+            if (A.ab) reinterpret_cast<double2 *>(A.ab)[o2] = make_double2(r.y, 0.0);
+            continue;
+        }
         // ---- discrete search over the sampled surface (first minimum on ties) ----
         int kb = 0;
         {

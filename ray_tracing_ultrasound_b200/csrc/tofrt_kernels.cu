@@ -173,6 +173,7 @@ struct tofrt_ctx {
     double *d_d1 = nullptr;   // Fermat solver: |A_e - P_j|/c1, built lazily per setup
     // 3-D two-point solve (tofrt_fermat3d_setup)
     bool f3_ready = false;
+    bool f3_inplane = false;    // pairs in the plane y = 0 are solved by the 2-D solver's arithmetic (same aperture)
     tofrt_surf3d f3_S{};
     int f3_E = 0, f3_n = 0;
     double f3_cell = 0.0;
@@ -1166,6 +1167,12 @@ int tofrt_fermat3d_setup(tofrt_ctx *c, const double *ang, int n_side, const doub
     S.h0 = c->S.h0; S.surface = c->S.surface;
     S.lo = ang[0]; S.hi = ang[n_side - 1];
     c->f3_S = S; c->f3_E = E3; c->f3_n = n_side;
+    {   // in-plane pairs go to the 2-D solve only when both solvers search the same aperture
+        double a_ends[2];
+        CUDA_TRY(cudaMemcpy(&a_ends[0], c->d_alpha, sizeof(double), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(&a_ends[1], c->d_alpha + (c->K - 1), sizeof(double), cudaMemcpyDeviceToHost));
+        c->f3_inplane = a_ends[0] == S.lo && a_ends[1] == S.hi && c->n_shooters >= 1;
+    }
     c->f3_cell = (S.hi - S.lo) / (n_side - 1);
     F3dArgs A{};
     A.ang = c->f3_geo; A.ex = c->f3_geo + n_side; A.ey = c->f3_geo + n_side + E3;
@@ -1196,6 +1203,7 @@ int tofrt_fermat3d_dev(tofrt_ctx *c, const double *d_fx, const double *d_fy, con
     A.ang = c->f3_geo; A.ex = c->f3_geo + n; A.ey = c->f3_geo + n + E3;
     A.E = E3; A.n_side = n; A.z_el = c->params_d; A.cell = c->f3_cell;
     A.tof = d_tof; A.kmin = d_kmin; A.ab = d_ab;
+    A.alpha2d = c->f3_inplane ? c->d_alpha : nullptr;
     cudaError_t ce;
     A.counter = c->take_counter(st, &ce);
     CUDA_TRY(ce);
@@ -1203,7 +1211,7 @@ int tofrt_fermat3d_dev(tofrt_ctx *c, const double *d_fx, const double *d_fy, con
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tofrt_fermat3d_kernel, kF3dThreads, smem));
     const long long items = ((F + kF3dThreads - 1) / kF3dThreads) * E3;
     int grid = (int)std::min<long long>((long long)c->sm_count * std::max(1, occ), items);
-    tofrt_fermat3d_kernel<<<grid, kF3dThreads, smem, st>>>(c->f3_S, A);
+    tofrt_fermat3d_kernel<<<grid, kF3dThreads, smem, st>>>(c->f3_S, A, c->S);
     CUDA_TRY(cudaGetLastError());
     return TOFRT_OK;
 }

@@ -348,7 +348,8 @@ class TofEngine:
 
     def fermat3d_tof(self, fx, fy, fz, with_kmin=True, with_angles=False):
         """One-way travel time element -> lens -> voxel for every (element, voxel) pair:
-        (tof[E3, F][, kmin[E3, F]][, ab[E3, F, 2]]), host arrays."""
+        (tof[E3, F][, kmin[E3, F]][, ab[E3, F, 2]]), host arrays.  Pairs in the plane y = 0 are solved by the 2-D
+        solver (fermat_tof) when both search the same aperture: kmin = -1 - j, ab = (alpha, 0); see include/tofrt.h."""
         fx, fy, fz = _f64(fx).ravel(), _f64(fy).ravel(), _f64(fz).ravel()
         if not (fx.shape == fy.shape == fz.shape):
             raise ValueError("fx, fy and fz must have the same length")

@@ -68,6 +68,30 @@ def test_twin_plane_y0_is_the_2d_problem(oracle_dm):
             assert abs(tof[e, f] - r.fun * 1e-4) < 1e-17
 
 
+def test_twin_2d_solver_matches_numpy_oracle_and_the_in_plane_rule(oracle_dm):
+    """The 2-D two-point twin (tofo_fermat2d) against the NumPy/SciPy oracle built from the reference's primitives, and
+    the in-plane rule of the 3-D twin: with the 2-D lens angles given, pairs at y = 0 return the 2-D solver's bits."""
+    from fermat_oracle import fermat_table
+    p, lens = oracle_dm.params(), Lens()
+    alpha = rs.launch_angles()
+    x_a, z_a = rs.transducer()
+    rng = np.random.default_rng(4)
+    fx, fz = rng.uniform(-0.04, 0.04, 25), rng.uniform(-0.01, 0.045, 25)
+    xe = x_a[::8]
+    tof, kmin, al = oracle_dm.fermat2d(p, alpha, xe, float(rs.D), fx, fz)
+    o_tof, o_k, o_al, gap = fermat_table(lens, alpha, xe, float(rs.D), fx, fz)
+    assert np.abs(tof - o_tof).max() < 1e-15 and np.abs(al - o_al).max() < 1e-8
+    assert np.array_equal(kmin[gap > 1e-18], o_k[gap > 1e-18])
+    ang = np.linspace(alpha[0], alpha[-1], 17)
+    ey = np.zeros(len(xe)); ey[1::2] = 3e-4
+    t3, k3, ab, ev, _ = oracle_dm.fermat3d(p, ang, xe, ey, float(rs.D), fx, np.zeros(25), fz, alpha2d=alpha)
+    on = ey == 0.0
+    assert np.array_equal(t3[on], tof[on]) and np.array_equal(k3[on], -1 - kmin[on]) and np.array_equal(ab[on][..., 0], al[on])
+    assert (k3[~on] >= 0).all() and (ev[~on] > 0).all()
+    free = oracle_dm.fermat3d(p, ang, xe, ey, float(rs.D), fx, np.zeros(25), fz)[0]
+    assert np.abs(free - t3).max() < 1e-17 and np.array_equal(free[~on], t3[~on])
+
+
 def test_twin_flat_interface_known_answer(oracle_dm):
     """Flat interface z = h0 in 3-D: for a voxel straight below an element the entry point is straight above it and
     the time is (d - h0)/c1 + (h0 - z)/c2; off-axis pairs obey Snell's law (gradient zero at the entry point)."""

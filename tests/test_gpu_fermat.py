@@ -38,6 +38,18 @@ def test_fermat_matches_numpy_oracle(engine):
         assert (tof[e] <= t_samples.min(axis=0) + 1e-18).all()
 
 
+def test_fermat_bit_exact_vs_twin(engine, oracle_dm):
+    """Every (element, focal point) pair against the oracle's CPU twin of the kernel (tofo_fermat2d: the same
+    operations compiled by gcc): times, discrete minimisers and entry angles identical -- the kernel's FP32-screened
+    argmin is exactly the plain FP64 first minimum."""
+    x_a, z_a, alpha = _setup(engine)
+    rng = np.random.default_rng(17)
+    fx, fz = rng.uniform(-0.04, 0.04, 400), rng.uniform(-0.01, 0.045, 400)
+    tof, kmin, al = engine.fermat_tof(fx, fz, with_alpha=True)
+    o_t, o_k, o_al = oracle_dm.fermat2d(oracle_dm.params(), alpha, x_a, float(z_a[0]), fx, fz)
+    assert np.array_equal(kmin, o_k) and np.array_equal(tof, o_t) and np.array_equal(al, o_al)
+
+
 def test_fermat_known_answers(engine):
     x_a, z_a, alpha = _setup(engine)
     lens = Lens()

@@ -60,9 +60,11 @@ def test_fermat3d_matches_scipy_oracle(engine):
     assert np.abs(ab[..., 0] - o_a).max() < 1e-6 and np.abs(ab[..., 1] - o_b).max() < 1e-6
 
 
-def test_fermat3d_plane_y0_equals_2d_solver(engine):
-    """Consistency pin of SURVEY 8(d) config 5: restricted to the plane y = 0 the 3-D engine reproduces the
-    2-D two-point solve (same lens samples' surface, same minimum)."""
+def test_fermat3d_plane_y0_is_the_2d_solver_bit_for_bit(engine, oracle_dm):
+    """Consistency pin of SURVEY 8(d) config 5: restricted to the plane y = 0 the 3-D engine reproduces the 2-D engine
+    bit for bit -- pairs with element and voxel at y = 0 ARE the 2-D problem and run the 2-D solver's arithmetic
+    (kmin = -1 - j names the 2-D lens sample); pairs off the plane are untouched; the CPU twin follows the same rule;
+    and the genuinely 3-D solve of the same in-plane pairs (twin without the rule) agrees to 1e-17 s."""
     x_a, z_a = rs.transducer()
     alpha, zf = rs.launch_angles(), rs.focus_line()
     engine.setup(alpha, zf, x_a[32], z_a[32], x_a)
@@ -71,8 +73,26 @@ def test_fermat3d_plane_y0_equals_2d_solver(engine):
     t2, k2, al2 = engine.fermat_tof(fx, fz, with_alpha=True)
     engine.setup_fermat3d(x_a, np.zeros_like(x_a), n_side=17)
     t3, k3, ab = engine.fermat3d_tof(fx, np.zeros_like(fx), fz, with_angles=True)
-    assert np.abs(t3 - t2).max() < 1e-17
-    assert np.abs(ab[..., 1]).max() < 1e-12 and np.abs(ab[..., 0] - al2).max() < 1e-7
+    assert np.array_equal(t3, t2) and np.array_equal(k3, -1 - k2)
+    assert np.array_equal(ab[..., 0], al2) and not ab[..., 1].any()
+    # a matrix array with one row on y = 0, voxels on and off the plane: mixed table against the twin
+    ex = np.concatenate([x_a[::8], x_a[::8]]); ey = np.concatenate([np.zeros(len(x_a[::8])), np.full(len(x_a[::8]), 6e-4)])
+    gy = np.where(np.arange(200) % 2 == 0, 0.0, rng.uniform(-0.02, 0.02, 200))
+    engine.setup_fermat3d(ex, ey, n_side=17)
+    t, k, ab = engine.fermat3d_tof(fx, gy, fz, with_angles=True)
+    p = oracle_dm.params()
+    o_t, o_k, o_ab, _, gap = oracle_dm.fermat3d(p, engine.f3_ang, ex, ey, D, fx, gy, fz, alpha2d=alpha)
+    inplane = (ey[:, None] == 0.0) & (gy[None, :] == 0.0)
+    assert inplane.sum() == len(x_a[::8]) * 100 and (k[inplane] < 0).all() and (k[~inplane] >= 0).all()
+    same = k == o_k
+    assert same[inplane].all() and same.mean() > 0.98
+    assert np.array_equal(t[same], o_t[same]) and np.array_equal(ab[same], o_ab[same])
+    assert np.array_equal(t[: len(x_a[::8]), ::2], t2[::8, ::2])              # the y = 0 row is the linear-array table
+    free3d = oracle_dm.fermat3d(p, engine.f3_ang, ex, ey, D, fx, gy, fz)[0]    # no rule: 3-D Newton everywhere
+    assert np.abs(free3d - t)[inplane].max() < 1e-17
+    # a different aperture for the 3-D search: no dispatch (the two solvers would not search the same set)
+    engine.setup_fermat3d(x_a, np.zeros_like(x_a), ang=np.linspace(-0.5, 0.5, 17))
+    assert (engine.fermat3d_tof(fx, np.zeros_like(fx), fz)[1] >= 0).all()
 
 
 def test_fermat3d_known_answers(engine, oracle_dm):
