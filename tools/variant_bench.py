@@ -5,9 +5,8 @@
 import os, subprocess, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = {"base": (), "t896": ("TOFRT_THREADS_GUIDED=896",), "t768": ("TOFRT_THREADS_GUIDED=768",),
-            "t512x2": ("TOFRT_THREADS_GUIDED=512", "TOFRT_MIN_BLOCKS=2"), "w8": ("TOFRT_PRED_W=8", "TOFRT_PRED_STEPS=4"),
-            "w2": ("TOFRT_PRED_W=2", "TOFRT_PRED_STEPS=2")}
+VARIANTS = {"base": (), "t672x2": ("TOFRT_THREADS_GUIDED=672", "TOFRT_MIN_BLOCKS=2"), "t640x2": ("TOFRT_THREADS_GUIDED=640", "TOFRT_MIN_BLOCKS=2"),
+            "t768x2": ("TOFRT_THREADS_GUIDED=768", "TOFRT_MIN_BLOCKS=2"), "t512x3": ("TOFRT_THREADS_GUIDED=512", "TOFRT_MIN_BLOCKS=3")}
 VDIR = os.path.join(ROOT, "tools", "_variants")
 
 if sys.argv[1] == "build":
@@ -27,7 +26,7 @@ else:
     from ray_tracing_ultrasound_b200 import TofEngine, reference_setup as rs
     x_a, z_a = rs.transducer(num_elements=128); alpha, zf = rs.launch_angles(), rs.focus_line()
     eng = TofEngine(0).setup(alpha, zf, x_a[64], z_a[64], x_a)
-    radii, offsets = rs.synthetic_grid(256, 1024)
+    radii, offsets = rs.synthetic_grid(1024, 1024)
     r = torch.from_numpy(radii).cuda(); o = torch.from_numpy(offsets).cuda()
     out = {"variant": sys.argv[2], "info": eng.kernel_info()}
     for mode in ("guided+vector",):
@@ -36,7 +35,7 @@ else:
         for _ in range(4): eng.tof_table_cuda(r, o)
         torch.cuda.synchronize()
         ts = []
-        for _ in range(5):
+        for _ in range(7):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); t = eng.tof_table_cuda(r, o); e1.record(); torch.cuda.synchronize()
             ts.append(round(e0.elapsed_time(e1), 2))
