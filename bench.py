@@ -253,6 +253,15 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` typed by hand: become the launch line the driver uses (one rank per GPU)
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                  f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                                  "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
     # stdout carries exactly ONE JSON line: anything a library prints meanwhile (NCCL's version banner at the first
     # communicator, ...) goes to stderr -- file descriptor 1 is pointed at stderr until the line is written
     sys.stdout.flush()
