@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import subprocess
 
 import pytest
 
@@ -62,3 +63,25 @@ def test_reference_setup_matches_golden_inputs(golden):
     r, o = rs.sweep_grid()
     assert np.array_equal(r, golden["sweep"]["radius"]) and np.array_equal(o, golden["sweep"]["offset"])
     assert z_a[0] == 0.21 and rs.launch_angles()[452] == -1.1102230246251565e-16
+
+
+def build_c_example(tmp_path):
+    """examples/sweep.c against include/tofrt.h and libtofrt.so with a plain C99 compiler: the header is C, the
+    boundary needs nothing but pointers and sizes."""
+    from ray_tracing_ultrasound_b200 import _build
+    if _build.is_stale():
+        _build.build()
+    exe = str(tmp_path / "sweep_example")
+    libdir = os.path.dirname(_build.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "sweep.c"), "-L" + libdir, "-ltofrt", "-lm", "-o", exe], check=True)
+    return exe, dict(os.environ, LD_LIBRARY_PATH=libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+
+
+def test_c_example_compiles_as_c99_and_fails_loudly_without_gpu(tmp_path):
+    from ray_tracing_ultrasound_b200 import _capi
+    exe, env = build_c_example(tmp_path)
+    if _capi.load().tofrt_device_count() > 0:
+        pytest.skip("a GPU is present (tests/test_gpu_dropin.py runs the example)")
+    res = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=120)
+    assert res.returncode == 1 and "tofrt_create" in res.stderr and res.stdout == ""

@@ -109,3 +109,23 @@ def test_main_compare_roundtrip(tmp_path, golden, engine, capsys):
     first = raw.split(b"\r\n")[1].decode().split(",")
     want = str(cc["head_text"][1]).split(",")
     assert first[:4] == want[:4] and first[7] == want[7] == "nan"
+
+
+def test_c_example_runs_the_reference_sweep_through_the_c_abi(tmp_path, golden, engine):
+    """examples/sweep.c: main_rt.py's sweep from plain C (tofrt_setup + one tofrt_table_host call), its CSV against
+    the reference's database_2.csv fixture: same rows, same hitted flags, travel times within 1e-12 s."""
+    import subprocess
+    from test_capi import build_c_example
+    exe, env = build_c_example(tmp_path)
+    out = tmp_path / "database_c.csv"
+    res = subprocess.run([exe, str(out)], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.split() == "geometries 210 receivers 65 rows 13650 hits 498".split()
+    raw = out.read_bytes()
+    assert raw.count(b"\r\n") == 13650
+    rows = [r.split(",") for r in raw.decode().split("\r\n") if r]
+    db = golden["database_2"]
+    assert [int(r[0]) for r in rows] == db["elem_idx"].tolist()
+    assert np.abs(np.array([float(r[1]) for r in rows]) - db["offset"]).max() < 1e-17
+    assert [r[3] == "True" for r in rows] == db["hitted"].tolist()
+    assert np.abs(np.array([float(r[4]) for r in rows]) - db["tof_total"]).max() <= TOF_TOL
