@@ -486,6 +486,11 @@ def test_many_receivers(engine, oracle_dm, n_elements):
         assert int(t.hit.sum()) > 500
         assert np.array_equal(t.k_hit, k_hit.T) and np.array_equal(t.tof, tof.T)
     engine.set_search("guided")
+    # the hit list of such a setup takes the dense route (no per-row slots with the state in global memory)
+    g, e, k, th = engine.tof_hits(radii, offsets)
+    gg, ee = np.nonzero(t.hit)
+    assert np.array_equal(g, gg) and np.array_equal(e, ee) and np.array_equal(k, t.k_hit[gg, ee])
+    assert np.array_equal(th, t.tof[gg, ee])
     from ray_tracing_ultrasound_b200 import TofrtError
     import torch
     if n_elements >= 4096:
