@@ -142,4 +142,38 @@ for i in range(n8):
 eng.set_small_g(True)
 out["small_g_vs_regular_kernel"] = {"batches": n8, "geometries": tot, "rays": tot * len(alpha), "mismatches": bad,
                                     "seconds": round(time.time() - t0, 1)}
+# (7) random setups (as in (3)): small-G mode vs regular kernel and hit list vs dense table, random batch sizes,
+#     one to three shooters
+n9 = int(os.environ.get("FUZZ_MODE_SETUPS", "40"))
+bad = 0; rows = 0; hits = 0; t0 = time.time()
+for i in range(n9):
+    r9 = np.random.default_rng(7000 + i)
+    kw = dict(c1=r9.uniform(3000, 7000), c2=r9.uniform(900, 2500), l0=r9.uniform(0.05, 0.2), h0=r9.uniform(0.04, 0.12))
+    K = int(r9.integers(64, 2000)); nel = int(r9.choice([16, 64, 128, 256]))
+    d = float(np.float64(kw["l0"]) + np.float64(kw["h0"]))
+    xa, _ = rs.transducer(num_elements=nel, pitch=np.float64(r9.uniform(2e-4, 8e-4)), d=d)
+    al = np.linspace(-r9.uniform(0.3, 0.85), r9.uniform(0.3, 0.85), K)
+    ns = int(r9.integers(1, 4)); sh = r9.integers(0, len(xa), ns)
+    rtol, atol = 10.0 ** r9.uniform(-7, -4), 10.0 ** r9.uniform(-7, -3)
+    eng.setup(al, np.ones(K) * d, xa[sh] if ns > 1 else xa[sh[0]], np.full(ns, d) if ns > 1 else d, xa, rtol=rtol, atol=atol, **kw)
+    n = int(r9.integers(1, 3000)) if i % 2 else int(r9.integers(30000, 90000))
+    rr, oo = r9.uniform(0.05, 1.1, n) * kw["h0"], r9.uniform(-0.3, 0.3, n) * kw["h0"]
+    rd, od = torch.from_numpy(rr).cuda(), torch.from_numpy(oo).cuda()
+    eng.set_small_g(True); a = eng.tof_table_cuda(rd, od)
+    eng.set_small_g(False); b = eng.tof_table_cuda(rd, od)
+    eng.set_small_g(True)
+    torch.cuda.synchronize()
+    bad += int((a.tof != b.tof).sum()) + int((a.k_hit != b.k_hit).sum())
+    hg, he, hk, ht = eng.tof_hits(rr, oo)
+    kh = a.k_hit.reshape(-1, len(xa)); tf = a.tof.reshape(-1, len(xa))
+    gg, ee = torch.nonzero(kh >= 0, as_tuple=True)
+    same = (len(hg) == len(gg) and np.array_equal(hg, gg.cpu().numpy()) and np.array_equal(he, ee.cpu().numpy()) and
+            np.array_equal(hk, kh[gg, ee].cpu().numpy()) and np.array_equal(ht, tf[gg, ee].cpu().numpy()))
+    bad += 0 if same else 1
+    rows += n * ns; hits += len(hg)
+    del a, b
+out["random_setups_modes"] = {"setups": n9, "rows": rows, "hits": hits, "mismatches": bad,
+                              "checked": "small-G mode = regular kernel; hit list = dense table; 1-3 shooters, batches of 1-3000 and 30000-90000 geometries",
+                              "seconds": round(time.time() - t0, 1)}
+eng.setup(alpha, zf, x_a[64], z_a[64], x_a)
 print(json.dumps(out, indent=1))
